@@ -1,0 +1,146 @@
+"""ctypes binding of libkatimager_b200.so (the C ABI in include/katimager_b200.h).
+
+There is deliberately no fallback: if the shared library has not been built
+(``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C
+katsdpimager_b200/csrc``) importing any operation raises, and if no CUDA device
+is usable the first runtime call raises.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
+                    c_uint32, c_ulonglong, c_void_p)
+
+LIB_NAME = 'libkatimager_b200.so'
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+_vp = c_void_p
+_i = c_int
+_i64 = c_int64
+_d = c_double
+_f = c_float
+_sz = c_size_t
+
+#: name -> argument types; every entry point returns int (0 = success) except
+#: kib_version / kib_last_error.  Kept in the order of include/katimager_b200.h.
+SIGNATURES = {
+    'kib_device_count': [POINTER(c_int)],
+    'kib_set_device': [_i],
+    'kib_get_device': [POINTER(c_int)],
+    'kib_device_name': [_i, c_char_p, _i],
+    'kib_device_attr': [_i, _i, POINTER(c_int64)],
+    'kib_mem_info': [POINTER(c_size_t), POINTER(c_size_t)],
+    'kib_stream_create': [POINTER(c_void_p)],
+    'kib_stream_destroy': [_vp],
+    'kib_stream_sync': [_vp],
+    'kib_stream_wait_event': [_vp, _vp],
+    'kib_event_create': [POINTER(c_void_p)],
+    'kib_event_record': [_vp, _vp],
+    'kib_event_sync': [_vp],
+    'kib_event_query': [_vp, POINTER(c_int)],
+    'kib_event_elapsed_ms': [_vp, _vp, POINTER(c_float)],
+    'kib_event_destroy': [_vp],
+    'kib_malloc': [POINTER(c_void_p), _sz],
+    'kib_free': [_vp],
+    'kib_host_alloc': [POINTER(c_void_p), _sz],
+    'kib_host_free': [_vp],
+    'kib_memset_async': [_vp, _i, _sz, _vp],
+    'kib_memcpy_h2d_async': [_vp, _vp, _sz, _vp],
+    'kib_memcpy_d2h_async': [_vp, _vp, _sz, _vp],
+    'kib_memcpy_d2d_async': [_vp, _vp, _sz, _vp],
+    'kib_memcpy3d_async': [_vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _sz, _i, _vp],
+    'kib_fft_plan2d_create': [POINTER(c_void_p), _i, _i, _i, _i],
+    'kib_fft_plan2d_exec': [_vp, _vp, _vp, _i, _vp],
+    'kib_fft_plan2d_destroy': [_vp],
+    'kib_grid': [_vp, _i, _i64, _i, _i,
+                 _vp, _i, _i64,
+                 _vp, _vp, _vp,
+                 _vp, _i, _i,
+                 _i, _i, _i, _i,
+                 _i64, _vp, _vp],
+    'kib_degrid': [_vp, _i, _i64, _i, _i,
+                   _vp, _vp, _vp, _vp,
+                   _vp, _i, _i,
+                   _i, _i, _i, _i,
+                   _i64, _vp, _vp],
+    'kib_grid_to_layer': [_vp, _i, _i, _vp, _i, _i, _i, _vp],
+    'kib_layer_to_grid': [_vp, _i, _i, _vp, _i, _i, _i, _vp],
+    'kib_layer_to_image': [_vp, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
+    'kib_image_to_layer': [_vp, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
+    'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
+    'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
+    'kib_apply_primary_beam': [_vp, _i, _i64, _vp, _i, _i, _i, _d, _d, _i, _vp],
+    'kib_update_tiles': [_vp, _i, _i64, _i, _i, _i, _i, _i,
+                         _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'kib_find_peak': [_vp, _i, _i64, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    'kib_subtract_psf': [_vp, _vp, _i, _i64, _i, _i, _i,
+                         _vp, _i, _i64, _i, _i, _i, _i,
+                         _vp, _i, _i, _d, _i, _vp],
+    'kib_clean_minor_cycles': [_vp, _vp, _i, _i64, _i, _i, _i, _i, _i,
+                               _vp, _i, _i64, _i, _i, _i, _i,
+                               _vp, _vp, _i, _i, _i,
+                               _vp, _vp, _vp,
+                               _d, _d, _i,
+                               _vp, _i, _vp, _i, _vp],
+    'kib_psf_patch': [_vp, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _i, _vp],
+    'kib_abs_histogram': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _vp, _i, _vp],
+    'kib_rank': [_vp, _i, _i64, _i, _i, _i, _i, _d, _vp, _i, _vp],
+    'kib_grid_weights': [_vp, _i, _i64, _i, _i, _vp, _vp, _i, _i64, _vp],
+    'kib_mean_weight': [_vp, _i, _i, _i, _vp, _vp],
+    'kib_density_weights': [_vp, _i, _i64, _i, _i, _i, _f, _f, _vp, _vp],
+    'kib_fill': [_vp, _i, _i64, _i, _i, _i, _d, _i, _vp],
+    'kib_predict': [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _f, _vp],
+    'kib_fp32_peak_kernel': [_vp, _i, _i, POINTER(c_double), _vp],
+}
+
+F32 = 0
+F64 = 1
+
+
+class KibError(RuntimeError):
+    """A call into libkatimager_b200.so failed."""
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            '{} has not been built; run `python -c "import __graft_entry__ as g; g.build()"` '
+            'in the repository root. There is no CPU fallback.'.format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.kib_version.restype = c_int
+    lib.kib_version.argtypes = []
+    lib.kib_last_error.restype = c_char_p
+    lib.kib_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().kib_last_error()
+        raise KibError('{} (code {})'.format(msg.decode('utf-8', 'replace') if msg else 'error', rc))
+
+
+def call(name, *args):
+    """Invoke entry point `name`, raising :class:`KibError` on failure."""
+    check(getattr(load(), name)(*args))
+
+
+def dtype_code(dtype):
+    import numpy as np
+    dtype = np.dtype(dtype)
+    if dtype in (np.float32, np.complex64):
+        return F32
+    if dtype in (np.float64, np.complex128):
+        return F64
+    raise TypeError('dtype {} is not supported'.format(dtype))

@@ -1,0 +1,691 @@
+// Hogbom CLEAN minor-cycle kernels for sm_100a.
+//
+// Replaces the operations of reference katsdpimager/clean.py (_UpdateTiles :398,
+// _FindPeak :516, _SubtractPsf :625, Clean :756, PsfPatch :72, NoiseEst :247) and
+// imager_kernels/clean/*.mako.  Results are bit-exact with the HOST classes
+// (CleanHost clean.py:971-1075, _tile_peak :946-968):
+//   * tile peak = first strict maximum in row-major order starting from best = 0;
+//     a tile without a positive metric stores 0 and the position (x0, y0) [sic];
+//   * global peak = first maximum over tiles in row-major tile order (np.argmax);
+//   * the SUMSQ metric and dirty -= (gain*peak)*psf use separately rounded multiplies
+//     and adds (numba / numpy do not contract to FMA).
+//
+// The reference syncs with the host on every minor cycle (clean.py:875-878).  Here a
+// whole batch of cycles runs device-resident: one `clean_step_kernel` launch per cycle
+// subtracts the PSF patch, recomputes the peaks of the 32x32 tiles it touched (from the
+// values still in registers) and the last block to finish selects the next global
+// peak, so no cycle ever waits for the host.
+#include "kib_common.cuh"
+#include <climits>
+
+namespace kib {
+
+constexpr int TILE = 32;
+constexpr int CLEAN_THREADS = 256;      // 32 x 8 threads, 4 rows of a tile each
+
+template <typename Real>
+struct Best {
+    Real value;
+    int key;   // tie-break: smaller key wins
+};
+
+template <typename Real>
+__device__ __forceinline__ Best<Real> better(Best<Real> a, Best<Real> b)
+{
+    return (b.value > a.value || (b.value == a.value && b.key < a.key)) ? b : a;
+}
+
+template <typename Real>
+__device__ __forceinline__ Best<Real> warp_best(Best<Real> v)
+{
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1) {
+        Best<Real> o;
+        o.value = __shfl_xor_sync(0xffffffffu, v.value, offset);
+        o.key = __shfl_xor_sync(0xffffffffu, v.key, offset);
+        v = better(v, o);
+    }
+    return v;
+}
+
+// Reduction over a block of up to 1024 threads; result valid in every thread.
+template <typename Real>
+__device__ __forceinline__ Best<Real> block_best(Best<Real> v, Best<Real> *scratch /* [33] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warps = (blockDim.x + 31) >> 5;
+    v = warp_best(v);
+    __syncthreads();        // protect scratch from a previous use
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        Best<Real> w;
+        w.value = -1;
+        w.key = INT_MAX;
+        if (lane < warps) w = scratch[lane];
+        w = warp_best(w);
+        if (lane == 0) scratch[32] = w;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+template <typename Real> __device__ __forceinline__ Real mul_rn_(Real a, Real b);
+template <> __device__ __forceinline__ float mul_rn_(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn_(double a, double b) { return __dmul_rn(a, b); }
+template <typename Real> __device__ __forceinline__ Real add_rn_(Real a, Real b);
+template <> __device__ __forceinline__ float add_rn_(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn_(double a, double b) { return __dadd_rn(a, b); }
+
+// Peak-finding metric of one pixel (clean.py:952-967; metric.mako)
+template <typename Real, int MODE>
+__device__ __forceinline__ Real clean_metric(const Real *pix, int P)
+{
+    if (MODE == KIB_CLEAN_I) return fabs(pix[0]);
+    Real value = 0;
+    for (int p = 0; p < P; p++) value = add_rn_(value, mul_rn_(pix[p], pix[p]));
+    return value;
+}
+
+// --------------------------------------------------------------------- update_tiles
+template <typename Real, int MODE>
+__global__ void __launch_bounds__(CLEAN_THREADS)
+update_tiles_kernel(const Real *__restrict__ dirty, int row_stride, long long pol_stride,
+                    int width, int height, int P, int border,
+                    Real *__restrict__ tile_max, int2 *__restrict__ tile_pos, int tile_stride,
+                    int tx0, int ty0)
+{
+    __shared__ Best<Real> scratch[33];
+    const int tx = tx0 + blockIdx.x, ty = ty0 + blockIdx.y;
+    const int x0 = tx * TILE + border, y0 = ty * TILE + border;
+    const int x1 = min(x0 + TILE, width - border), y1 = min(y0 + TILE, height - border);
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    Best<Real> best;
+    best.value = 0;
+    best.key = INT_MAX;
+    const int x = x0 + lx;
+#pragma unroll
+    for (int k = 0; k < TILE / 8; k++) {
+        const int y = y0 + ly + 8 * k;
+        if (x < x1 && y < y1) {
+            Real pix[4];
+            const long long addr = (long long) y * row_stride + x;
+            const int np = MODE == KIB_CLEAN_I ? 1 : P;
+            for (int p = 0; p < np; p++) pix[p] = dirty[p * pol_stride + addr];
+            const Real value = clean_metric<Real, MODE>(pix, P);
+            if (value > best.value) {
+                best.value = value;
+                best.key = y * width + x;
+            }
+        }
+    }
+    best = block_best(best, scratch);
+    if (threadIdx.x == 0) {
+        const long long idx = (long long) ty * tile_stride + tx;
+        tile_max[idx] = best.value;
+        // clean.py:950: a tile with no positive value reports (x0, y0)
+        tile_pos[idx] = best.key == INT_MAX ? make_int2(x0, y0)
+                                            : make_int2(best.key / width, best.key % width);
+    }
+}
+
+// ------------------------------------------------------------------------ find_peak
+// Body shared by the stand-alone kernel and the tail of clean_step_kernel.
+template <typename Real>
+__device__ __forceinline__ void find_peak_body(
+    const Real *dirty, int row_stride, long long pol_stride, int P,
+    const Real *tile_max, const int2 *tile_pos, int tile_stride, int tiles_x, int tiles_y,
+    Real *peak_value, int *peak_pos, Real *peak_pixel, Best<Real> *scratch)
+{
+    Best<Real> best;
+    best.value = -1;
+    best.key = INT_MAX;
+    const int total = tiles_x * tiles_y;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int ty = i / tiles_x, tx = i - ty * tiles_x;
+        const Real value = __ldcg(tile_max + (long long) ty * tile_stride + tx);
+        if (value > best.value) {      // i increases, so the first maximum is kept
+            best.value = value;
+            best.key = i;
+        }
+    }
+    best = block_best(best, scratch);
+    if (threadIdx.x == 0) {
+        int2 pos = make_int2(0, 0);
+        Real value = 0;
+        if (best.key != INT_MAX) {
+            const int ty = best.key / tiles_x, tx = best.key - ty * tiles_x;
+            pos = __ldcg(tile_pos + (long long) ty * tile_stride + tx);
+            value = best.value;
+        }
+        peak_value[0] = value;
+        peak_pos[0] = pos.x;    // row
+        peak_pos[1] = pos.y;    // column
+        for (int p = 0; p < P; p++)
+            peak_pixel[p] = __ldcg(dirty + p * pol_stride + (long long) pos.x * row_stride + pos.y);
+    }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(1024)
+find_peak_kernel(const Real *dirty, int row_stride, long long pol_stride, int P,
+                 const Real *tile_max, const int2 *tile_pos, int tile_stride,
+                 int tiles_x, int tiles_y, Real *peak_value, int *peak_pos, Real *peak_pixel)
+{
+    __shared__ Best<Real> scratch[33];
+    find_peak_body(dirty, row_stride, pol_stride, P, tile_max, tile_pos, tile_stride,
+                   tiles_x, tiles_y, peak_value, peak_pos, peak_pixel, scratch);
+}
+
+// --------------------------------------------------------------------- subtract_psf
+template <typename Real>
+__global__ void __launch_bounds__(256)
+subtract_psf_kernel(Real *__restrict__ dirty, Real *__restrict__ model,
+                    int row_stride, long long pol_stride, int width, int height, int P,
+                    const Real *__restrict__ psf, int psf_row_stride, long long psf_pol_stride,
+                    int psf_x0, int psf_y0, int patch_w, int patch_h,
+                    const Real *__restrict__ peak_pixel, int pos_y, int pos_x,
+                    int start_x, int start_y, Real loop_gain)
+{
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y;
+    if (gx == 0 && gy == 0) {
+        for (int p = 0; p < P; p++) {
+            const long long c = p * pol_stride + (long long) pos_y * row_stride + pos_x;
+            model[c] = add_rn_(model[c], mul_rn_(loop_gain, peak_pixel[p]));
+        }
+    }
+    if (gx >= patch_w) return;
+    const int x = start_x + gx, y = start_y + gy;
+    if (x < 0 || x >= width || y < 0 || y >= height) return;
+    const long long addr = (long long) y * row_stride + x;
+    const long long paddr = (long long) (psf_y0 + gy) * psf_row_stride + psf_x0 + gx;
+    for (int p = 0; p < P; p++) {
+        const Real scale = mul_rn_(loop_gain, peak_pixel[p]);
+        const Real d = dirty[p * pol_stride + addr];
+        dirty[p * pol_stride + addr] = add_rn_(d, -mul_rn_(scale, psf[p * psf_pol_stride + paddr]));
+    }
+}
+
+// ------------------------------------------------------------- device-resident cycle
+struct CleanStepParams {
+    void *dirty;
+    void *model;
+    const void *psf;
+    void *tile_max;
+    int2 *tile_pos;
+    void *peak_value;
+    int *peak_pos;
+    void *peak_pixel;
+    void *components;
+    int *state;           // [0] cycles done, [1] stopped by threshold, [2] block ticket
+    long long pol_stride;
+    long long psf_pol_stride;
+    double loop_gain;
+    double threshold;
+    int row_stride, width, height, border;
+    int psf_row_stride, psf_width, psf_height;
+    int patch_w, patch_h;
+    int tile_stride, tiles_x, tiles_y;
+    int component_stride;   // bytes
+    int max_components;
+};
+
+__device__ __forceinline__ int floordiv32(int a) { return a >> 5; }   // arithmetic shift = floor
+
+template <typename Real, int P, int MODE>
+__global__ void __launch_bounds__(CLEAN_THREADS)
+clean_step_kernel(const CleanStepParams prm)
+{
+    __shared__ Best<Real> scratch[33];
+    __shared__ int is_last;
+    int *state = prm.state;
+    // Uniform across the grid: state[1] is only ever written by launches in which every
+    // block takes the "below threshold" exit.
+    if (__ldcg(state + 1) != 0) return;
+    Real *const peak_value = static_cast<Real *>(prm.peak_value);
+    Real *const peak_pixel = static_cast<Real *>(prm.peak_pixel);
+    const Real pv = __ldcg(peak_value);
+    const int done = __ldcg(state);
+    if ((double) pv < prm.threshold || done >= prm.max_components) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (double) pv < prm.threshold)
+            state[1] = 1;
+        return;
+    }
+    const int pos_y = __ldcg(prm.peak_pos), pos_x = __ldcg(prm.peak_pos + 1);
+    Real scale[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) scale[p] = mul_rn_((Real) prm.loop_gain, __ldcg(peak_pixel + p));
+
+    Real *const dirty = static_cast<Real *>(prm.dirty);
+    const Real *const psf = static_cast<const Real *>(prm.psf);
+    const int W = prm.width, H = prm.height, border = prm.border;
+    // Patch rectangle (clean.py:1024-1043), clipped to the image
+    const int px0 = pos_x - prm.patch_w / 2, py0 = pos_y - prm.patch_h / 2;
+    const int cx0 = max(px0, 0), cy0 = max(py0, 0);
+    const int cx1 = min(px0 + prm.patch_w, W), cy1 = min(py0 + prm.patch_h, H);
+    const int psf_x0 = prm.psf_width / 2 - prm.patch_w / 2 - px0;    // psf x = image x + psf_x0
+    const int psf_y0 = prm.psf_height / 2 - prm.patch_h / 2 - py0;
+    // This block's cell of the tile lattice (extended over the border region)
+    const int cell_x = floordiv32(cx0 - border) + blockIdx.x;
+    const int cell_y = floordiv32(cy0 - border) + blockIdx.y;
+    const int rx0 = border + cell_x * TILE, ry0 = border + cell_y * TILE;
+    const bool is_tile = cell_x >= 0 && cell_x < prm.tiles_x && cell_y >= 0 && cell_y < prm.tiles_y;
+    const bool touches = rx0 < cx1 && rx0 + TILE > cx0 && ry0 < cy1 && ry0 + TILE > cy0;
+
+    if (touches) {
+        const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+        const int x = rx0 + lx;
+        Best<Real> best;
+        best.value = 0;
+        best.key = INT_MAX;
+        const bool x_in_patch = x >= cx0 && x < cx1;
+        const bool x_in_tile = is_tile && x >= border && x < W - border;
+#pragma unroll
+        for (int k = 0; k < TILE / 8; k++) {
+            const int y = ry0 + ly + 8 * k;
+            const bool in_patch = x_in_patch && y >= cy0 && y < cy1;
+            const bool in_tile = x_in_tile && y >= border && y < H - border;
+            if (in_patch || in_tile) {
+                const long long addr = (long long) y * prm.row_stride + x;
+                Real pix[P];
+                if (in_patch) {
+                    const long long paddr = (long long) (y + psf_y0) * prm.psf_row_stride + x + psf_x0;
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        const Real d = dirty[p * prm.pol_stride + addr];
+                        const Real s = __ldg(psf + p * prm.psf_pol_stride + paddr);
+                        pix[p] = add_rn_(d, -mul_rn_(scale[p], s));
+                        dirty[p * prm.pol_stride + addr] = pix[p];
+                    }
+                } else {
+                    const int np = MODE == KIB_CLEAN_I ? 1 : P;
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        if (p < np) pix[p] = dirty[p * prm.pol_stride + addr];
+                }
+                if (in_tile) {
+                    const Real value = clean_metric<Real, MODE>(pix, P);
+                    if (value > best.value) {
+                        best.value = value;
+                        best.key = y * W + x;
+                    }
+                }
+            }
+        }
+        if (is_tile) {
+            best = block_best(best, scratch);
+            if (threadIdx.x == 0) {
+                const long long idx = (long long) cell_y * prm.tile_stride + cell_x;
+                static_cast<Real *>(prm.tile_max)[idx] = best.value;
+                prm.tile_pos[idx] = best.key == INT_MAX ? make_int2(rx0, ry0)
+                                                        : make_int2(best.key / W, best.key % W);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        // model image and component list (clean.py:1047, :882; imaging.py:389-396)
+        Real *const model = static_cast<Real *>(prm.model);
+        char *rec = static_cast<char *>(prm.components) + (long long) done * prm.component_stride;
+        reinterpret_cast<int *>(rec)[0] = pos_y;
+        reinterpret_cast<int *>(rec)[1] = pos_x;
+        Real *vals = reinterpret_cast<Real *>(rec + 8);
+        vals[0] = pv;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const long long c = p * prm.pol_stride + (long long) pos_y * prm.row_stride + pos_x;
+            model[c] = add_rn_(model[c], scale[p]);
+            vals[1 + p] = scale[p];
+        }
+        state[0] = done + 1;
+    }
+    // Last block to finish selects the next peak.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(state + 2, 1);
+        is_last = ticket == (int) (gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        find_peak_body(dirty, prm.row_stride, prm.pol_stride, P,
+                       static_cast<const Real *>(prm.tile_max), prm.tile_pos, prm.tile_stride,
+                       prm.tiles_x, prm.tiles_y, peak_value, prm.peak_pos, peak_pixel, scratch);
+        if (threadIdx.x == 0) state[2] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------ psf_patch
+template <typename Real>
+__global__ void __launch_bounds__(256)
+psf_patch_kernel(const Real *__restrict__ psf, int row_stride, long long pol_stride, int P,
+                 int min_x, int min_y, int max_x, int max_y, int mid_x, int mid_y,
+                 Real threshold, int *__restrict__ bound)
+{
+    const int x = min_x + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = min_y + blockIdx.y;
+    int dx = 0, dy = 0;
+    if (x <= max_x && y <= max_y) {
+        bool over = false;
+        for (int p = 0; p < P; p++)
+            over |= fabs(psf[p * pol_stride + (long long) y * row_stride + x]) >= threshold;
+        if (over) {
+            dx = abs(x - mid_x);
+            dy = abs(y - mid_y);
+        }
+    }
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1) {
+        dx = max(dx, __shfl_xor_sync(0xffffffffu, dx, offset));
+        dy = max(dy, __shfl_xor_sync(0xffffffffu, dy, offset));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (dx > 0) atomicMax(bound, dx);
+        if (dy > 0) atomicMax(bound + 1, dy);
+    }
+}
+
+// ------------------------------------------------------------------- noise estimate
+__global__ void __launch_bounds__(256)
+abs_histogram_kernel(const float *__restrict__ image, int row_stride, long long pol_stride,
+                     int inner_w, int inner_h, int P, int border,
+                     unsigned prefix, int prefix_shift, int use_prefix, int shift, unsigned mask,
+                     unsigned *__restrict__ hist)
+{
+    extern __shared__ unsigned local[];
+    for (unsigned i = threadIdx.x; i <= mask; i += blockDim.x) local[i] = 0;
+    __syncthreads();
+    const long long total = (long long) inner_w * inner_h * P;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long) gridDim.x * blockDim.x) {
+        const int x = (int) (i % inner_w);
+        const long long r = i / inner_w;
+        const int y = (int) (r % inner_h);
+        const int p = (int) (r / inner_h);
+        const float v = image[p * pol_stride + (long long) (y + border) * row_stride + x + border];
+        const unsigned bits = __float_as_uint(fabsf(v));
+        if (!use_prefix || (bits >> prefix_shift) == prefix)
+            atomicAdd(&local[(bits >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i <= mask; i += blockDim.x)
+        if (local[i] != 0) atomicAdd(&hist[i], local[i]);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+rank_kernel(const Real *__restrict__ image, int row_stride, long long pol_stride,
+            int inner_w, int inner_h, int P, int border, Real value,
+            unsigned long long *__restrict__ rank)
+{
+    const long long total = (long long) inner_w * inner_h * P;
+    unsigned count = 0;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long) gridDim.x * blockDim.x) {
+        const int x = (int) (i % inner_w);
+        const long long r = i / inner_w;
+        const int y = (int) (r % inner_h);
+        const int p = (int) (r / inner_h);
+        const Real v = image[p * pol_stride + (long long) (y + border) * row_stride + x + border];
+        count += fabs(v) < value;
+    }
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1)
+        count += __shfl_xor_sync(0xffffffffu, count, offset);
+    if ((threadIdx.x & 31) == 0 && count != 0) atomicAdd(rank, (unsigned long long) count);
+}
+
+template <typename Real, int P>
+static void launch_step_mode(const CleanStepParams &prm, int mode, dim3 grid, cudaStream_t stream)
+{
+    if (mode == KIB_CLEAN_I)
+        clean_step_kernel<Real, P, KIB_CLEAN_I><<<grid, CLEAN_THREADS, 0, stream>>>(prm);
+    else
+        clean_step_kernel<Real, P, KIB_CLEAN_SUMSQ><<<grid, CLEAN_THREADS, 0, stream>>>(prm);
+}
+
+template <typename Real>
+static int launch_step(const CleanStepParams &prm, int P, int mode, dim3 grid, cudaStream_t stream)
+{
+    switch (P) {
+    case 1: launch_step_mode<Real, 1>(prm, mode, grid, stream); break;
+    case 2: launch_step_mode<Real, 2>(prm, mode, grid, stream); break;
+    case 3: launch_step_mode<Real, 3>(prm, mode, grid, stream); break;
+    case 4: launch_step_mode<Real, 4>(prm, mode, grid, stream); break;
+    default:
+        set_error("kib_clean_minor_cycles: num_pols must be 1..4, not %d", P);
+        return -1;
+    }
+    return 0;
+}
+
+}  // namespace kib
+
+using namespace kib;
+
+#define KIB_CHECK_DTYPE(name)                                                        \
+    KIB_REQUIRE(dtype == KIB_F32 || dtype == KIB_F64, name ": bad dtype %d", dtype)
+#define KIB_CHECK_MODE(name)                                                         \
+    KIB_REQUIRE(mode == KIB_CLEAN_I || mode == KIB_CLEAN_SUMSQ, name ": bad clean mode %d", mode)
+
+extern "C" {
+
+int kib_update_tiles(const void *dirty, int row_stride, int64_t pol_stride,
+                     int width, int height, int num_pols, int border, int mode,
+                     void *tile_max, int32_t *tile_pos, int tile_stride,
+                     int tx0, int ty0, int tx1, int ty1, int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_update_tiles");
+    KIB_CHECK_MODE("kib_update_tiles");
+    KIB_REQUIRE(num_pols >= 1 && num_pols <= 4, "kib_update_tiles: num_pols must be 1..4");
+    if (tx0 >= tx1 || ty0 >= ty1) return 0;
+    dim3 g(tx1 - tx0, ty1 - ty0, 1);
+    cudaStream_t s = as_stream(stream);
+    int2 *pos = reinterpret_cast<int2 *>(tile_pos);
+#define LAUNCH(REAL, MODE)                                                                   \
+    update_tiles_kernel<REAL, MODE><<<g, CLEAN_THREADS, 0, s>>>(                             \
+        static_cast<const REAL *>(dirty), row_stride, pol_stride, width, height, num_pols,   \
+        border, static_cast<REAL *>(tile_max), pos, tile_stride, tx0, ty0)
+    if (dtype == KIB_F32) {
+        if (mode == KIB_CLEAN_I) LAUNCH(float, KIB_CLEAN_I); else LAUNCH(float, KIB_CLEAN_SUMSQ);
+    } else {
+        if (mode == KIB_CLEAN_I) LAUNCH(double, KIB_CLEAN_I); else LAUNCH(double, KIB_CLEAN_SUMSQ);
+    }
+#undef LAUNCH
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_find_peak(const void *dirty, int row_stride, int64_t pol_stride, int num_pols,
+                  const void *tile_max, const int32_t *tile_pos, int tile_stride,
+                  int tiles_x, int tiles_y,
+                  void *peak_value, int32_t *peak_pos, void *peak_pixel,
+                  int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_find_peak");
+    KIB_REQUIRE(tiles_x > 0 && tiles_y > 0, "kib_find_peak: empty tile array");
+    const int2 *pos = reinterpret_cast<const int2 *>(tile_pos);
+    if (dtype == KIB_F32)
+        find_peak_kernel<float><<<1, 1024, 0, as_stream(stream)>>>(
+            static_cast<const float *>(dirty), row_stride, pol_stride, num_pols,
+            static_cast<const float *>(tile_max), pos, tile_stride, tiles_x, tiles_y,
+            static_cast<float *>(peak_value), peak_pos, static_cast<float *>(peak_pixel));
+    else
+        find_peak_kernel<double><<<1, 1024, 0, as_stream(stream)>>>(
+            static_cast<const double *>(dirty), row_stride, pol_stride, num_pols,
+            static_cast<const double *>(tile_max), pos, tile_stride, tiles_x, tiles_y,
+            static_cast<double *>(peak_value), peak_pos, static_cast<double *>(peak_pixel));
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_subtract_psf(void *dirty, void *model, int row_stride, int64_t pol_stride,
+                     int width, int height, int num_pols,
+                     const void *psf, int psf_row_stride, int64_t psf_pol_stride,
+                     int psf_width, int psf_height,
+                     int patch_width, int patch_height,
+                     const void *peak_pixel, int pos_y, int pos_x, double loop_gain,
+                     int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_subtract_psf");
+    KIB_REQUIRE(patch_width >= 1 && patch_height >= 1 && patch_width <= psf_width
+                && patch_height <= psf_height, "kib_subtract_psf: bad patch %d x %d",
+                patch_width, patch_height);
+    const int psf_x0 = psf_width / 2 - patch_width / 2;
+    const int psf_y0 = psf_height / 2 - patch_height / 2;
+    const int start_x = pos_x - patch_width / 2, start_y = pos_y - patch_height / 2;
+    dim3 g(divup(patch_width, 256), patch_height, 1);
+    if (dtype == KIB_F32)
+        subtract_psf_kernel<float><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float *>(dirty), static_cast<float *>(model), row_stride, pol_stride,
+            width, height, num_pols, static_cast<const float *>(psf), psf_row_stride,
+            psf_pol_stride, psf_x0, psf_y0, patch_width, patch_height,
+            static_cast<const float *>(peak_pixel), pos_y, pos_x, start_x, start_y,
+            (float) loop_gain);
+    else
+        subtract_psf_kernel<double><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double *>(dirty), static_cast<double *>(model), row_stride, pol_stride,
+            width, height, num_pols, static_cast<const double *>(psf), psf_row_stride,
+            psf_pol_stride, psf_x0, psf_y0, patch_width, patch_height,
+            static_cast<const double *>(peak_pixel), pos_y, pos_x, start_x, start_y, loop_gain);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol_stride,
+                           int width, int height, int num_pols, int border, int mode,
+                           const void *psf, int psf_row_stride, int64_t psf_pol_stride,
+                           int psf_width, int psf_height,
+                           int patch_width, int patch_height,
+                           void *tile_max, int32_t *tile_pos, int tile_stride,
+                           int tiles_x, int tiles_y,
+                           void *peak_value, int32_t *peak_pos, void *peak_pixel,
+                           double loop_gain, double threshold, int max_cycles,
+                           void *components, int component_stride, int32_t *state,
+                           int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_clean_minor_cycles");
+    KIB_CHECK_MODE("kib_clean_minor_cycles");
+    KIB_REQUIRE(patch_width >= 1 && patch_height >= 1 && patch_width <= psf_width
+                && patch_height <= psf_height, "kib_clean_minor_cycles: bad patch %d x %d",
+                patch_width, patch_height);
+    const int real_size = dtype == KIB_F32 ? 4 : 8;
+    KIB_REQUIRE(component_stride >= 8 + real_size * (1 + num_pols),
+                "kib_clean_minor_cycles: component stride %d too small", component_stride);
+    KIB_REQUIRE(state != nullptr && components != nullptr, "kib_clean_minor_cycles: null state");
+    if (max_cycles <= 0) return 0;
+    CleanStepParams prm;
+    prm.dirty = dirty;
+    prm.model = model;
+    prm.psf = psf;
+    prm.tile_max = tile_max;
+    prm.tile_pos = reinterpret_cast<int2 *>(tile_pos);
+    prm.peak_value = peak_value;
+    prm.peak_pos = peak_pos;
+    prm.peak_pixel = peak_pixel;
+    prm.components = components;
+    prm.state = state;
+    prm.pol_stride = pol_stride;
+    prm.psf_pol_stride = psf_pol_stride;
+    prm.loop_gain = loop_gain;
+    prm.threshold = threshold;
+    prm.row_stride = row_stride;
+    prm.width = width;
+    prm.height = height;
+    prm.border = border;
+    prm.psf_row_stride = psf_row_stride;
+    prm.psf_width = psf_width;
+    prm.psf_height = psf_height;
+    prm.patch_w = patch_width;
+    prm.patch_h = patch_height;
+    prm.tile_stride = tile_stride;
+    prm.tiles_x = tiles_x;
+    prm.tiles_y = tiles_y;
+    prm.component_stride = component_stride;
+    prm.max_components = max_cycles;
+    // A patch of width w starting anywhere touches at most (w - 1) / 32 + 2 lattice cells.
+    dim3 g((patch_width - 1) / TILE + 2, (patch_height - 1) / TILE + 2, 1);
+    cudaStream_t s = as_stream(stream);
+    for (int i = 0; i < max_cycles; i++) {
+        int rc = dtype == KIB_F32 ? launch_step<float>(prm, num_pols, mode, g, s)
+                                  : launch_step<double>(prm, num_pols, mode, g, s);
+        if (rc != 0) return rc;
+    }
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_psf_patch(const void *psf, int row_stride, int64_t pol_stride, int num_pols,
+                  int min_x, int min_y, int max_x, int max_y, int mid_x, int mid_y,
+                  double threshold, int32_t *bound, int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_psf_patch");
+    KIB_REQUIRE(bound != nullptr, "kib_psf_patch: null bound");
+    cudaStream_t s = as_stream(stream);
+    KIB_CUDA(cudaMemsetAsync(bound, 0, 2 * sizeof(int32_t), s));
+    if (max_x < min_x || max_y < min_y) return 0;
+    dim3 g(divup(max_x - min_x + 1, 256), max_y - min_y + 1, 1);
+    if (dtype == KIB_F32)
+        psf_patch_kernel<float><<<g, 256, 0, s>>>(
+            static_cast<const float *>(psf), row_stride, pol_stride, num_pols,
+            min_x, min_y, max_x, max_y, mid_x, mid_y, (float) threshold, bound);
+    else
+        psf_patch_kernel<double><<<g, 256, 0, s>>>(
+            static_cast<const double *>(psf), row_stride, pol_stride, num_pols,
+            min_x, min_y, max_x, max_y, mid_x, mid_y, threshold, bound);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_abs_histogram(const void *image, int row_stride, int64_t pol_stride,
+                      int width, int height, int num_pols, int border,
+                      uint32_t prefix, int prefix_bits, int shift, int bits,
+                      uint32_t *hist, int dtype, kib_stream_t stream)
+{
+    KIB_REQUIRE(dtype == KIB_F32, "kib_abs_histogram: only float32 images are supported");
+    KIB_REQUIRE(bits >= 1 && bits <= 12 && shift >= 0 && shift + bits <= 32,
+                "kib_abs_histogram: bad digit (shift %d, bits %d)", shift, bits);
+    KIB_REQUIRE(prefix_bits >= 0 && prefix_bits + shift + bits <= 32,
+                "kib_abs_histogram: bad prefix");
+    const int inner_w = width - 2 * border, inner_h = height - 2 * border;
+    if (inner_w <= 0 || inner_h <= 0) return 0;
+    const unsigned mask = (1u << bits) - 1;
+    const long long total = (long long) inner_w * inner_h * num_pols;
+    int blocks = (int) ((total + 256 * 16 - 1) / (256 * 16));
+    const int max_blocks = sm_count() * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    abs_histogram_kernel<<<blocks, 256, (mask + 1) * sizeof(unsigned), as_stream(stream)>>>(
+        static_cast<const float *>(image), row_stride, pol_stride, inner_w, inner_h, num_pols,
+        border, prefix, shift + bits, prefix_bits > 0, shift, mask, hist);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_rank(const void *image, int row_stride, int64_t pol_stride,
+             int width, int height, int num_pols, int border, double value,
+             unsigned long long *rank, int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_rank");
+    const int inner_w = width - 2 * border, inner_h = height - 2 * border;
+    if (inner_w <= 0 || inner_h <= 0) return 0;
+    const long long total = (long long) inner_w * inner_h * num_pols;
+    int blocks = (int) ((total + 256 * 16 - 1) / (256 * 16));
+    const int max_blocks = sm_count() * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    if (dtype == KIB_F32)
+        rank_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(
+            static_cast<const float *>(image), row_stride, pol_stride, inner_w, inner_h,
+            num_pols, border, (float) value, rank);
+    else
+        rank_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>(
+            static_cast<const double *>(image), row_stride, pol_stride, inner_w, inner_h,
+            num_pols, border, value, rank);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

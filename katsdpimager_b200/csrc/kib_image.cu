@@ -1,0 +1,382 @@
+// Grid <-> image stage kernels for sm_100a (everything around the cuFFT call).
+//
+// Replaces GridToImage._run / ImageToGrid._run (reference katsdpimager/image.py:649-673,
+// 716-740), layer_to_image.mako / image_to_layer.mako / layer_image.mako, scale.mako,
+// add_image.mako and apply_primary_beam.mako.  Numerics follow GridToImageHost /
+// ImageToGridHost (image.py:781-799, 836-848): direction cosines are evaluated in the
+// image precision with separately rounded multiply and add (numpy semantics, no FMA),
+// so n = sqrt(1 - (l^2 + m^2)) is bit-identical to the host; the W phase w*(n-1) is
+// formed and range-reduced in double precision (the reference's frontend passes w as
+// a float64 scalar, which promotes the host computation the same way).
+//
+// All kernels are HBM-bound streaming passes: one thread per (pair of) element(s),
+// fully coalesced rows, no shared memory.
+#include "kib_common.cuh"
+
+namespace kib {
+
+template <typename Real> struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<double> { typedef double2 type; };
+
+// ------------------------------------------------------------ grid -> layer (pad + ifftshift)
+template <typename Complex>
+__global__ void __launch_bounds__(256)
+grid_to_layer_kernel(Complex *__restrict__ layer, int layer_row_stride, int N,
+                     const Complex *__restrict__ grid, int grid_row_stride, int G)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= N) return;
+    const int half = G / 2;
+    // Layer index f in [0, half) holds non-negative frequencies (grid index f + half);
+    // [N - half, N) holds negative frequencies (grid index f - (N - half)).
+    int gy = -1, gx = -1;
+    if (y < half) gy = y + half;
+    else if (y >= N - half) gy = y - (N - half);
+    if (x < half) gx = x + half;
+    else if (x >= N - half) gx = x - (N - half);
+    Complex value;
+    value.x = 0;
+    value.y = 0;
+    if (gy >= 0 && gx >= 0) value = grid[(long long) gy * grid_row_stride + gx];
+    layer[(long long) y * layer_row_stride + x] = value;
+}
+
+template <typename Complex>
+__global__ void __launch_bounds__(256)
+layer_to_grid_kernel(Complex *__restrict__ grid, int grid_row_stride, int G,
+                     const Complex *__restrict__ layer, int layer_row_stride, int N)
+{
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y;
+    if (gx >= G) return;
+    const int half = G / 2;
+    const int y = gy >= half ? gy - half : gy + (N - half);
+    const int x = gx >= half ? gx - half : gx + (N - half);
+    grid[(long long) gy * grid_row_stride + gx] = layer[(long long) y * layer_row_stride + x];
+}
+
+// ------------------------------------------------------------ layer <-> image
+template <typename Real> __device__ __forceinline__ Real mul_rn(Real a, Real b);
+template <> __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+template <typename Real> __device__ __forceinline__ Real add_rn(Real a, Real b);
+template <> __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// exp(2 pi i * sign * w * (n - 1)) with the argument reduced in double precision
+template <typename Real>
+__device__ __forceinline__ void w_rotation(Real n, double w, Real *c, Real *s);
+
+template <>
+__device__ __forceinline__ void w_rotation<float>(float n, double w, float *c, float *s)
+{
+    const double phase = w * (double) __fadd_rn(n, -1.0f);
+    const float r = (float) (phase - rint(phase));
+    sincospif(2.0f * r, s, c);
+}
+
+template <>
+__device__ __forceinline__ void w_rotation<double>(double n, double w, double *c, double *s)
+{
+    const double phase = w * (n - 1.0);
+    const double r = phase - rint(phase);
+    sincospi(2.0 * r, s, c);
+}
+
+// One thread handles the four pixels (x, y), (x + h, y), (x, y + h), (x + h, y + h),
+// h = size / 2, which map to the four layer elements at the same offsets with the halves
+// swapped (fftshift); they share kernel1d / l^2 / m^2 values.
+template <typename Real, bool TO_IMAGE>
+__global__ void __launch_bounds__(256)
+layer_image_kernel(Real *__restrict__ image, int image_row_stride,
+                   typename Vec2<Real>::type *__restrict__ layer, int layer_row_stride,
+                   int half, const Real *__restrict__ kernel1d,
+                   Real lm_scale, Real lm_bias, double w)
+{
+    typedef typename Vec2<Real>::type Complex;
+    const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= half || y0 >= half) return;
+    int xs[2] = {x0, x0 + half};
+    int ys[2] = {y0, y0 + half};
+    Real kx[2], ky[2], l2[2], m2[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        kx[i] = kernel1d[xs[i]];
+        ky[i] = kernel1d[ys[i]];
+        const Real l = add_rn(mul_rn((Real) xs[i], lm_scale), lm_bias);
+        const Real m = add_rn(mul_rn((Real) ys[i], lm_scale), lm_bias);
+        l2[i] = mul_rn(l, l);
+        m2[i] = mul_rn(m, m);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const long long iaddr = (long long) ys[i] * image_row_stride + xs[j];
+            const long long laddr = (long long) ys[1 - i] * layer_row_stride + xs[1 - j];
+            const Real n = sqrt(add_rn((Real) 1, -add_rn(m2[i], l2[j])));
+            Real c, s;
+            w_rotation<Real>(n, w, &c, &s);
+            if (TO_IMAGE) {
+                const Complex v = layer[laddr];
+                // Re(v * exp(2 pi i w (n - 1))) * n / (ky * kx)
+                const Real rotated = v.x * c - v.y * s;
+                image[iaddr] += rotated * n / (ky[i] * kx[j]);
+            } else {
+                // image / (ky * kx * n) * exp(-2 pi i w (n - 1))
+                const Real v = image[iaddr] / (ky[i] * kx[j] * n);
+                Complex out;
+                out.x = v * c;
+                out.y = -(v * s);
+                layer[laddr] = out;
+            }
+        }
+}
+
+// ------------------------------------------------------------ elementwise image ops
+struct ScaleFactors {
+    double v[4];
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+scale_kernel(Real *__restrict__ image, int row_stride, long long pol_stride, int width, int height,
+             int num_pols, ScaleFactors scale)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= width) return;
+    long long addr = (long long) y * row_stride + x;
+    for (int p = 0; p < num_pols; p++, addr += pol_stride)
+        image[addr] *= (Real) scale.v[p];
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+add_image_kernel(Real *__restrict__ dest, int dest_row_stride, long long dest_pol_stride,
+                 const Real *__restrict__ src, int src_row_stride, long long src_pol_stride,
+                 int width, int height, int num_pols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= width) return;
+    long long d = (long long) y * dest_row_stride + x;
+    long long s = (long long) y * src_row_stride + x;
+    for (int p = 0; p < num_pols; p++, d += dest_pol_stride, s += src_pol_stride)
+        dest[d] += src[s];
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+apply_primary_beam_kernel(Real *__restrict__ image, int row_stride, long long pol_stride,
+                          const Real *__restrict__ beam_power, int width, int height,
+                          int num_pols, Real threshold, Real replacement)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= width) return;
+    long long addr = (long long) y * row_stride + x;
+    const Real beam = beam_power[addr];
+    const bool low = beam < threshold;
+    for (int p = 0; p < num_pols; p++, addr += pol_stride)
+        image[addr] = low ? replacement : image[addr] / beam;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+fill_kernel(Real *__restrict__ data, int row_stride, long long pol_stride, int width, int height,
+            int num_pols, Real value)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= width) return;
+    long long addr = (long long) y * row_stride + x;
+    for (int p = 0; p < num_pols; p++, addr += pol_stride)
+        data[addr] = value;
+}
+
+static dim3 row_grid(int width, int height) { return dim3(divup(width, 256), height, 1); }
+
+}  // namespace kib
+
+using namespace kib;
+
+#define KIB_CHECK_DTYPE(name)                                                        \
+    KIB_REQUIRE(dtype == KIB_F32 || dtype == KIB_F64, name ": bad dtype %d", dtype)
+
+extern "C" {
+
+int kib_grid_to_layer(void *layer, int layer_row_stride, int layer_size,
+                      const void *grid_plane, int grid_row_stride, int grid_size,
+                      int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_grid_to_layer");
+    KIB_REQUIRE(grid_size % 2 == 0 && grid_size <= layer_size && grid_size > 0,
+                "kib_grid_to_layer: grid size %d must be even and no larger than layer size %d",
+                grid_size, layer_size);
+    dim3 g = row_grid(layer_size, layer_size);
+    if (dtype == KIB_F32)
+        grid_to_layer_kernel<float2><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float2 *>(layer), layer_row_stride, layer_size,
+            static_cast<const float2 *>(grid_plane), grid_row_stride, grid_size);
+    else
+        grid_to_layer_kernel<double2><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double2 *>(layer), layer_row_stride, layer_size,
+            static_cast<const double2 *>(grid_plane), grid_row_stride, grid_size);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_layer_to_grid(void *grid_plane, int grid_row_stride, int grid_size,
+                      const void *layer, int layer_row_stride, int layer_size,
+                      int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_layer_to_grid");
+    KIB_REQUIRE(grid_size % 2 == 0 && grid_size <= layer_size && grid_size > 0,
+                "kib_layer_to_grid: grid size %d must be even and no larger than layer size %d",
+                grid_size, layer_size);
+    dim3 g = row_grid(grid_size, grid_size);
+    if (dtype == KIB_F32)
+        layer_to_grid_kernel<float2><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float2 *>(grid_plane), grid_row_stride, grid_size,
+            static_cast<const float2 *>(layer), layer_row_stride, layer_size);
+    else
+        layer_to_grid_kernel<double2><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double2 *>(grid_plane), grid_row_stride, grid_size,
+            static_cast<const double2 *>(layer), layer_row_stride, layer_size);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_layer_to_image(void *image_plane, int image_row_stride,
+                       const void *layer, int layer_row_stride, int size,
+                       const void *kernel1d, double lm_scale, double lm_bias, double w,
+                       int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_layer_to_image");
+    KIB_REQUIRE(size > 0 && size % 2 == 0, "kib_layer_to_image: image size must be even, not %d", size);
+    const int half = size / 2;
+    dim3 block(32, 8, 1);
+    dim3 g(divup(half, 32), divup(half, 8), 1);
+    if (dtype == KIB_F32)
+        layer_image_kernel<float, true><<<g, block, 0, as_stream(stream)>>>(
+            static_cast<float *>(image_plane), image_row_stride,
+            static_cast<float2 *>(const_cast<void *>(layer)), layer_row_stride, half,
+            static_cast<const float *>(kernel1d), (float) lm_scale, (float) lm_bias, w);
+    else
+        layer_image_kernel<double, true><<<g, block, 0, as_stream(stream)>>>(
+            static_cast<double *>(image_plane), image_row_stride,
+            static_cast<double2 *>(const_cast<void *>(layer)), layer_row_stride, half,
+            static_cast<const double *>(kernel1d), lm_scale, lm_bias, w);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_image_to_layer(void *layer, int layer_row_stride,
+                       const void *image_plane, int image_row_stride, int size,
+                       const void *kernel1d, double lm_scale, double lm_bias, double w,
+                       int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_image_to_layer");
+    KIB_REQUIRE(size > 0 && size % 2 == 0, "kib_image_to_layer: image size must be even, not %d", size);
+    const int half = size / 2;
+    dim3 block(32, 8, 1);
+    dim3 g(divup(half, 32), divup(half, 8), 1);
+    if (dtype == KIB_F32)
+        layer_image_kernel<float, false><<<g, block, 0, as_stream(stream)>>>(
+            static_cast<float *>(const_cast<void *>(image_plane)), image_row_stride,
+            static_cast<float2 *>(layer), layer_row_stride, half,
+            static_cast<const float *>(kernel1d), (float) lm_scale, (float) lm_bias, w);
+    else
+        layer_image_kernel<double, false><<<g, block, 0, as_stream(stream)>>>(
+            static_cast<double *>(const_cast<void *>(image_plane)), image_row_stride,
+            static_cast<double2 *>(layer), layer_row_stride, half,
+            static_cast<const double *>(kernel1d), lm_scale, lm_bias, w);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_scale(void *image, int row_stride, int64_t pol_stride, int width, int height,
+              int num_pols, const double *scale, int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_scale");
+    KIB_REQUIRE(num_pols >= 1 && num_pols <= 4, "kib_scale: num_pols must be 1..4");
+    KIB_REQUIRE(scale != nullptr, "kib_scale: null scale");
+    if (width <= 0 || height <= 0) return 0;
+    ScaleFactors f = {{0, 0, 0, 0}};
+    for (int p = 0; p < num_pols; p++) f.v[p] = scale[p];
+    dim3 g = row_grid(width, height);
+    if (dtype == KIB_F32)
+        scale_kernel<float><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float *>(image), row_stride, pol_stride, width, height, num_pols, f);
+    else
+        scale_kernel<double><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double *>(image), row_stride, pol_stride, width, height, num_pols, f);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_add_image(void *dest, int dest_row_stride, int64_t dest_pol_stride,
+                  const void *src, int src_row_stride, int64_t src_pol_stride,
+                  int width, int height, int num_pols, int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_add_image");
+    if (width <= 0 || height <= 0) return 0;
+    dim3 g = row_grid(width, height);
+    if (dtype == KIB_F32)
+        add_image_kernel<float><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float *>(dest), dest_row_stride, dest_pol_stride,
+            static_cast<const float *>(src), src_row_stride, src_pol_stride,
+            width, height, num_pols);
+    else
+        add_image_kernel<double><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double *>(dest), dest_row_stride, dest_pol_stride,
+            static_cast<const double *>(src), src_row_stride, src_pol_stride,
+            width, height, num_pols);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_apply_primary_beam(void *image, int row_stride, int64_t pol_stride,
+                           const void *beam_power, int width, int height, int num_pols,
+                           double threshold, double replacement, int dtype,
+                           kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_apply_primary_beam");
+    if (width <= 0 || height <= 0) return 0;
+    dim3 g = row_grid(width, height);
+    if (dtype == KIB_F32)
+        apply_primary_beam_kernel<float><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float *>(image), row_stride, pol_stride,
+            static_cast<const float *>(beam_power), width, height, num_pols,
+            (float) threshold, (float) replacement);
+    else
+        apply_primary_beam_kernel<double><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double *>(image), row_stride, pol_stride,
+            static_cast<const double *>(beam_power), width, height, num_pols,
+            threshold, replacement);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_fill(void *data, int row_stride, int64_t pol_stride, int width, int height,
+             int num_pols, double value, int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_fill");
+    if (width <= 0 || height <= 0) return 0;
+    dim3 g = row_grid(width, height);
+    if (dtype == KIB_F32)
+        fill_kernel<float><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float *>(data), row_stride, pol_stride, width, height, num_pols,
+            (float) value);
+    else
+        fill_kernel<double><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double *>(data), row_stride, pol_stride, width, height, num_pols, value);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

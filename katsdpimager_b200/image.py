@@ -1,0 +1,335 @@
+"""Image-domain operations and the grid <-> image conversion on B200.
+
+Same surface as the reference's :mod:`katsdpimager.image` (reference image.py:15-740):
+``LayerToImage`` / ``ImageToLayer``, ``Scale``, ``AddImage``, ``ApplyPrimaryBeam`` and the
+compound ``GridToImage`` / ``ImageToGrid`` built by ``GridImageTemplate``.  The 2-D
+transform itself is cuFFT (:mod:`.fft`); everything around it runs in the fused
+kernels of csrc/kib_image.cu:
+
+* grid -> layer: zero fill, zero padding and ifftshift of one polarization plane in a
+  single pass (the reference issues a memset and four strided copies, image.py:659-671);
+* layer -> image: fftshift, W-term rotation, n-term and taper division, accumulation.
+"""
+import numpy as np
+
+from . import _lib, accel, fft
+from .profiling import profile_device
+from .types import real_to_complex
+
+
+class _LayerImageTemplate:
+    """Base of :class:`LayerToImageTemplate` and :class:`ImageToLayerTemplate`
+    (reference image.py:15-86 documents the mathematics)."""
+
+    def __init__(self, context, real_dtype, tuning=None):
+        _lib.load()
+        self.context = context
+        self.real_dtype = np.dtype(real_dtype)
+
+
+class _LayerImage(accel.Operation):
+    """Conversion between a corner-centred complex *layer* and one polarization
+    plane of a centred real *image* (reference image.py:89-180).
+
+    .. rubric:: Slots
+
+    **layer** : complex, height x width
+    **image** : real, polarizations x height x width
+    **kernel1d** : real, width -- image-plane taper of the gridding kernel
+    """
+
+    _entry = None
+
+    def __init__(self, template, command_queue, shape, lm_scale, lm_bias, allocator=None):
+        if len(shape) != 3 or shape[-1] != shape[-2]:
+            raise ValueError('shape must be square, not {}'.format(shape))
+        if shape[-1] % 2 != 0:
+            raise ValueError('image size must be even, not {}'.format(shape[-1]))
+        super().__init__(command_queue, allocator)
+        self.template = template
+        dims = [accel.Dimension(x) for x in shape]
+        self.slots['layer'] = accel.IOSlot(dims[-2:], real_to_complex(template.real_dtype))
+        self.slots['image'] = accel.IOSlot(dims, template.real_dtype)
+        self.slots['kernel1d'] = accel.IOSlot((shape[-1],), template.real_dtype)
+        self.lm_scale = lm_scale
+        self.lm_bias = lm_bias
+        self.w = 0
+        self.polarization = 0
+
+    def set_w(self, w):
+        """Set the W coordinate of the layer (wavelengths)."""
+        self.w = w
+
+    def set_polarization(self, polarization):
+        if polarization < 0 or polarization >= self.slots['image'].shape[0]:
+            raise IndexError('polarization index out of range')
+        self.polarization = polarization
+
+    def _run(self):
+        layer = self.buffer('layer')
+        image = self.buffer('image')
+        kernel1d = self.buffer('kernel1d')
+        itemsize = image.dtype.itemsize
+        plane = image.padded_shape[1] * image.padded_shape[2]
+        image_ptr = (image.ptr.value or 0) + self.polarization * plane * itemsize
+        size = image.shape[-1]
+        with profile_device(self.command_queue, self._entry[4:]):
+            if self._entry == 'kib_layer_to_image':
+                _lib.call(self._entry, image_ptr, image.padded_shape[2],
+                          layer.ptr, layer.padded_shape[1], size, kernel1d.ptr,
+                          float(self.lm_scale), float(self.lm_bias), float(self.w),
+                          _lib.dtype_code(image.dtype), self.command_queue.stream)
+            else:
+                _lib.call(self._entry, layer.ptr, layer.padded_shape[1],
+                          image_ptr, image.padded_shape[2], size, kernel1d.ptr,
+                          float(self.lm_scale), float(self.lm_bias), float(self.w),
+                          _lib.dtype_code(image.dtype), self.command_queue.stream)
+
+
+class LayerToImageTemplate(_LayerImageTemplate):
+    def instantiate(self, *args, **kwargs):
+        return LayerToImage(self, *args, **kwargs)
+
+
+class LayerToImage(_LayerImage):
+    """image[pol] += Re(fftshift(layer) * exp(2 pi i w (n - 1))) * n / taper (accumulates)."""
+    _entry = 'kib_layer_to_image'
+
+
+class ImageToLayerTemplate(_LayerImageTemplate):
+    def instantiate(self, *args, **kwargs):
+        return ImageToLayer(self, *args, **kwargs)
+
+
+class ImageToLayer(_LayerImage):
+    """layer = ifftshift(image[pol] / (taper * n) * exp(-2 pi i w (n - 1)))."""
+    _entry = 'kib_image_to_layer'
+
+
+class _ImageOpTemplate:
+    def __init__(self, context, dtype, num_polarizations, tuning=None):
+        _lib.load()
+        self.context = context
+        self.dtype = np.dtype(dtype)
+        self.num_polarizations = num_polarizations
+
+
+def _check_image_shape(template, shape):
+    if len(shape) != 3:
+        raise ValueError('Wrong number of dimensions in shape')
+    if shape[0] != template.num_polarizations:
+        raise ValueError('Mismatch in number of polarizations')
+
+
+class ScaleTemplate(_ImageOpTemplate):
+    """Scale an image by a constant per polarization (reference image.py:281-367)."""
+
+    def instantiate(self, *args, **kwargs):
+        return Scale(self, *args, **kwargs)
+
+
+class Scale(accel.Operation):
+    """.. rubric:: Slots
+
+    **data** : real, polarizations x height x width, scaled in place
+    """
+
+    def __init__(self, template, command_queue, shape, allocator=None):
+        super().__init__(command_queue, allocator)
+        _check_image_shape(template, shape)
+        self.template = template
+        self.slots['data'] = accel.IOSlot(shape, template.dtype)
+        self.scale_factor = np.zeros((shape[0],), template.dtype)
+
+    def set_scale_factor(self, scale_factor):
+        self.scale_factor[:] = scale_factor
+
+    def _run(self):
+        data = self.buffer('data')
+        factors = np.ascontiguousarray(self.scale_factor, dtype=np.float64)
+        with profile_device(self.command_queue, 'scale'):
+            _lib.call('kib_scale', data.ptr, data.padded_shape[2],
+                      data.padded_shape[1] * data.padded_shape[2],
+                      data.shape[2], data.shape[1], data.shape[0],
+                      factors.ctypes.data_as(_lib.POINTER(_lib.c_double)),
+                      _lib.dtype_code(data.dtype), self.command_queue.stream)
+
+
+class AddImageTemplate(_ImageOpTemplate):
+    """Add one image to another (reference image.py:370-458)."""
+
+    def instantiate(self, *args, **kwargs):
+        return AddImage(self, *args, **kwargs)
+
+
+class AddImage(accel.Operation):
+    """.. rubric:: Slots
+
+    **src** : real image to add
+    **dest** : real image updated in place (may be padded differently from **src**)
+    """
+
+    def __init__(self, template, command_queue, shape, allocator=None):
+        super().__init__(command_queue, allocator)
+        _check_image_shape(template, shape)
+        self.template = template
+        self.slots['src'] = accel.IOSlot(shape, template.dtype)
+        self.slots['dest'] = accel.IOSlot(shape, template.dtype)
+
+    def _run(self):
+        src = self.buffer('src')
+        dest = self.buffer('dest')
+        with profile_device(self.command_queue, 'add_image'):
+            _lib.call('kib_add_image',
+                      dest.ptr, dest.padded_shape[2], dest.padded_shape[1] * dest.padded_shape[2],
+                      src.ptr, src.padded_shape[2], src.padded_shape[1] * src.padded_shape[2],
+                      src.shape[2], src.shape[1], src.shape[0],
+                      _lib.dtype_code(dest.dtype), self.command_queue.stream)
+
+
+class ApplyPrimaryBeamTemplate(_ImageOpTemplate):
+    """Divide an image by a polarization-independent primary beam
+    (reference image.py:461-558)."""
+
+    def instantiate(self, *args, **kwargs):
+        return ApplyPrimaryBeam(self, *args, **kwargs)
+
+
+class ApplyPrimaryBeam(accel.Operation):
+    """.. rubric:: Slots
+
+    **data** : real image, divided in place; pixels where the beam power is below
+    `threshold` are set to `replacement`
+    **beam_power** : real, height x width
+    """
+
+    def __init__(self, template, command_queue, shape, threshold, replacement, allocator=None):
+        super().__init__(command_queue, allocator)
+        _check_image_shape(template, shape)
+        self.template = template
+        y_dim = accel.Dimension(shape[1])
+        x_dim = accel.Dimension(shape[2])
+        self.slots['data'] = accel.IOSlot((shape[0], y_dim, x_dim), template.dtype)
+        self.slots['beam_power'] = accel.IOSlot((y_dim, x_dim), template.dtype)
+        self.threshold = threshold
+        self.replacement = replacement
+
+    def _run(self):
+        data = self.buffer('data')
+        beam_power = self.buffer('beam_power')
+        assert beam_power.padded_shape == data.padded_shape[1:]
+        with profile_device(self.command_queue, 'apply_primary_beam'):
+            _lib.call('kib_apply_primary_beam', data.ptr, data.padded_shape[2],
+                      data.padded_shape[1] * data.padded_shape[2], beam_power.ptr,
+                      data.shape[2], data.shape[1], data.shape[0],
+                      float(self.threshold), float(self.replacement),
+                      _lib.dtype_code(data.dtype), self.command_queue.stream)
+
+
+class GridImageTemplate:
+    """Conversion between a centred complex UV grid and a centred real image via an
+    unnormalised complex 2-D FFT (reference image.py:561-606)."""
+
+    def __init__(self, context, real_dtype):
+        self.context = context
+        self.real_dtype = np.dtype(real_dtype)
+        self.layer_to_image = LayerToImageTemplate(context, real_dtype)
+        self.image_to_layer = ImageToLayerTemplate(context, real_dtype)
+
+    def make_fft_plan(self, shape_layer, padded_shape_layer):
+        complex_dtype = real_to_complex(self.real_dtype)
+        return fft.FftTemplate(self.context, 2, shape_layer, complex_dtype, complex_dtype,
+                               padded_shape_layer, padded_shape_layer)
+
+    def instantiate_grid_to_image(self, *args, **kwargs):
+        return GridToImage(self, *args, **kwargs)
+
+    def instantiate_image_to_grid(self, *args, **kwargs):
+        return ImageToGrid(self, *args, **kwargs)
+
+
+def _check_grid(grid, layer):
+    polarizations, height, width = grid.shape
+    if height % 2 or width % 2 or height != width:
+        raise ValueError('grid must be square with even size, not {}'.format(grid.shape))
+    if width > layer.shape[-1]:
+        raise ValueError('grid is larger than the image')
+    return polarizations, width
+
+
+class GridToImage(accel.OperationSequence):
+    """grid -> image for every polarization (reference image.py:609-673).
+
+    .. rubric:: Slots
+
+    **grid** : complex, polarizations x G x G;  **layer** : complex N x N scratch;
+    **image** : real, polarizations x N x N (accumulated into);  **kernel1d** : real N
+    """
+
+    def __init__(self, template, command_queue, shape_grid,
+                 lm_scale, lm_bias, fft_plan, allocator=None):
+        self._ifft = fft_plan.instantiate(command_queue, fft.FftMode.INVERSE, allocator)
+        shape_image = (shape_grid[0],) + tuple(fft_plan.shape)
+        self._layer_to_image = template.layer_to_image.instantiate(
+            command_queue, shape_image, lm_scale, lm_bias, allocator)
+        operations = [('ifft', self._ifft), ('layer_to_image', self._layer_to_image)]
+        compounds = {
+            'layer': ['ifft:src', 'ifft:dest', 'layer_to_image:layer'],
+            'image': ['layer_to_image:image'],
+            'kernel1d': ['layer_to_image:kernel1d']
+        }
+        super().__init__(command_queue, operations, compounds, allocator=allocator)
+        self.slots['grid'] = accel.IOSlot(shape_grid, fft_plan.dtype_src)
+
+    def set_w(self, w):
+        self._layer_to_image.set_w(w)
+
+    def _run(self):
+        grid = self.buffer('grid')
+        layer = self.buffer('layer')
+        polarizations, size = _check_grid(grid, layer)
+        plane_bytes = grid.padded_shape[1] * grid.padded_shape[2] * grid.dtype.itemsize
+        for pol in range(polarizations):
+            with profile_device(self.command_queue, 'grid_to_layer'):
+                _lib.call('kib_grid_to_layer', layer.ptr, layer.padded_shape[1], layer.shape[1],
+                          (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
+                          _lib.dtype_code(grid.dtype), self.command_queue.stream)
+            self._layer_to_image.set_polarization(pol)
+            super()._run()
+
+
+class ImageToGrid(accel.OperationSequence):
+    """image -> grid for every polarization (reference image.py:676-740); slots as
+    :class:`GridToImage` with **grid** as the output."""
+
+    def __init__(self, template, command_queue, shape_grid,
+                 lm_scale, lm_bias, fft_plan, allocator=None):
+        shape_image = (shape_grid[0],) + tuple(fft_plan.shape)
+        self._fft = fft_plan.instantiate(command_queue, fft.FftMode.FORWARD, allocator)
+        self._image_to_layer = template.image_to_layer.instantiate(
+            command_queue, shape_image, lm_scale, lm_bias, allocator)
+        operations = [('image_to_layer', self._image_to_layer), ('fft', self._fft)]
+        compounds = {
+            'layer': ['fft:src', 'fft:dest', 'image_to_layer:layer'],
+            'image': ['image_to_layer:image'],
+            'kernel1d': ['image_to_layer:kernel1d']
+        }
+        super().__init__(command_queue, operations, compounds, allocator=allocator)
+        self.slots['grid'] = accel.IOSlot(shape_grid, fft_plan.dtype_dest)
+
+    def set_w(self, w):
+        self._image_to_layer.set_w(w)
+
+    def _run(self):
+        grid = self.buffer('grid')
+        layer = self.buffer('layer')
+        polarizations, size = _check_grid(grid, layer)
+        plane_bytes = grid.padded_shape[1] * grid.padded_shape[2] * grid.dtype.itemsize
+        for pol in range(polarizations):
+            self._image_to_layer.set_polarization(pol)
+            super()._run()
+            with profile_device(self.command_queue, 'layer_to_grid'):
+                _lib.call('kib_layer_to_grid',
+                          (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
+                          layer.ptr, layer.padded_shape[1], layer.shape[1],
+                          _lib.dtype_code(grid.dtype), self.command_queue.stream)

@@ -1,0 +1,388 @@
+"""Per-channel imaging facade: every operation of the hot path wired to shared buffers.
+
+Offers the API of the reference's :class:`katsdpimager.imaging.ImagingTemplate` /
+:class:`~katsdpimager.imaging.Imaging` (reference imaging.py:11-419) -- the object
+``frontend.process_channel`` drives (reference frontend.py:465-658) -- on top of the
+sm_100a operations in this package.  The reference file itself can also be used
+unchanged over these modules; this module additionally exposes
+the batched minor-cycle entry point :meth:`Imaging.clean_cycles`.
+
+Buffer sharing follows the reference (imaging.py:185-209): one ``uv`` / ``w_plane`` /
+``vis`` / ``weights`` staging set feeds weighting, prediction and gridding; the UV
+``grid`` feeds the FFT stage; ``dirty``, ``model`` and ``psf`` are shared by CLEAN,
+scaling, primary-beam correction and the noise estimate.
+"""
+import numpy as np
+
+from . import accel, clean, grid, image, predict, weight
+from .profiling import profile_device, profile_function
+
+
+class ImagingTemplate:
+    """Holds one template per operation (reference imaging.py:11-51)."""
+
+    @profile_function()
+    def __init__(self, context, array_parameters, fixed_image_parameters,
+                 weight_parameters, fixed_grid_parameters, clean_parameters, clean_tuning=None):
+        self.context = context
+        self.array_parameters = array_parameters
+        self.fixed_image_parameters = fixed_image_parameters
+        self.weight_parameters = weight_parameters
+        self.fixed_grid_parameters = fixed_grid_parameters
+        self.clean_parameters = clean_parameters
+        dtype = fixed_image_parameters.real_dtype
+        pols = len(fixed_image_parameters.polarizations)
+        self.weights = weight.WeightsTemplate(context, weight_parameters.weight_type, pols)
+        self.gridder = grid.GridderTemplate(context, fixed_image_parameters, fixed_grid_parameters)
+        self.predict = predict.PredictTemplate(context, dtype, pols)
+        self.grid_image = image.GridImageTemplate(context, dtype)
+        self.psf_patch = clean.PsfPatchTemplate(context, dtype, pols)
+        self.noise_est = clean.NoiseEstTemplate(context, dtype, pols)
+        self.clean = clean.CleanTemplate(context, clean_parameters, dtype, pols,
+                                         tuning=clean_tuning)
+        self.scale = image.ScaleTemplate(context, dtype, pols)
+        self.add_image = image.AddImageTemplate(context, dtype, pols)
+        self.apply_primary_beam = image.ApplyPrimaryBeamTemplate(context, dtype, pols)
+        self.degridder = None
+        if fixed_grid_parameters.degrid:
+            self.degridder = grid.DegridderTemplate(
+                context, fixed_image_parameters, fixed_grid_parameters)
+
+    def instantiate(self, *args, **kwargs):
+        return Imaging(self, *args, **kwargs)
+
+
+class _Staging:
+    """Pinned host mirror of a per-visibility slot plus the event that marks the end of
+    the last upload from it (it must not be overwritten before then)."""
+
+    def __init__(self, context, slot):
+        self.array = accel.HostArray(slot.shape, slot.dtype, slot.required_padded_shape(),
+                                     context=context)
+        self.transfer_event = None
+
+    def wait(self):
+        if self.transfer_event is not None:
+            self.transfer_event.wait()
+            self.transfer_event = None
+
+
+def _uv_view(coords):
+    """View the adjacent ``uv`` and ``sub_uv`` int16 pairs of a record array as N x 4."""
+    uv_type, uv_offset = coords.dtype.fields['uv'][:2]
+    sub_type, sub_offset = coords.dtype.fields['sub_uv'][:2]
+    pair = np.dtype(('i2', (2,)))
+    if uv_type != pair or sub_type != pair or sub_offset != uv_offset + pair.itemsize:
+        raise TypeError('uv and sub_uv must be adjacent pairs of int16')
+    quad = np.dtype(dict(names=['q'], formats=[('i2', (4,))], offsets=[uv_offset],
+                         itemsize=coords.dtype.itemsize))
+    return coords.view(quad)['q']
+
+
+#: compound slot -> member slots, as reference imaging.py:185-204
+_SHARED_SLOTS = {
+    'weights': ['weights:weights', 'predict:weights', 'continuum_predict:weights'],
+    'weights_grid': ['weights:grid', 'gridder:weights_grid'],
+    'uv': ['weights:uv', 'gridder:uv', 'predict:uv', 'continuum_predict:uv'],
+    'w_plane': ['gridder:w_plane', 'predict:w_plane', 'continuum_predict:w_plane'],
+    'vis': ['gridder:vis', 'predict:vis', 'continuum_predict:vis'],
+    'grid': ['gridder:grid', 'grid_to_image:grid'],
+    'layer': ['grid_to_image:layer'],
+    'dirty': ['grid_to_image:image', 'noise_est:dirty', 'clean:dirty', 'scale:data',
+              'add_image:dest', 'apply_primary_beam_dirty:data'],
+    'model': ['clean:model', 'apply_primary_beam_model:data', 'add_image:src'],
+    'psf': ['clean:psf', 'psf_patch:psf'],
+    'tile_max': ['clean:tile_max'],
+    'tile_pos': ['clean:tile_pos'],
+    'peak_value': ['clean:peak_value'],
+    'peak_pos': ['clean:peak_pos'],
+    'peak_pixel': ['clean:peak_pixel'],
+    'beam_power': ['apply_primary_beam_model:beam_power', 'apply_primary_beam_dirty:beam_power'],
+}
+
+
+class Imaging(accel.OperationSequence):
+    """All device state for imaging one channel (reference imaging.py:81-419)."""
+
+    @profile_function()
+    def __init__(self, template, command_queue, image_parameters, grid_parameters,
+                 max_vis, max_sources, major, allocator=None):
+        assert image_parameters.fixed == template.fixed_image_parameters
+        assert grid_parameters.fixed == template.fixed_grid_parameters
+        self.template = template
+        context = template.context
+        pixels = image_parameters.pixels
+        dtype = image_parameters.fixed.real_dtype
+        lm_scale = float(image_parameters.pixel_size)
+        lm_bias = -0.5 * pixels * lm_scale
+        image_shape = (len(image_parameters.fixed.polarizations), pixels, pixels)
+        fft_plan = template.grid_image.make_fft_plan(image_shape[1:], image_shape[1:])
+        degrid = bool(grid_parameters.fixed.degrid)
+
+        def instantiate(tmpl, *args):
+            return tmpl.instantiate(command_queue, *args, allocator)
+
+        self._gridder = instantiate(template.gridder, template.array_parameters,
+                                    image_parameters, grid_parameters, max_vis)
+        grid_shape = self._gridder.slots['grid'].shape
+        self._continuum_predict = instantiate(template.predict, image_parameters, grid_parameters,
+                                              max_vis, max_sources)
+        self._weights = instantiate(template.weights, grid_shape, max_vis)
+        self._weights.robustness = template.weight_parameters.robustness
+        self._grid_to_image = template.grid_image.instantiate_grid_to_image(
+            command_queue, grid_shape, lm_scale, lm_bias, fft_plan, allocator)
+        self._psf_patch = instantiate(template.psf_patch, image_shape)
+        self._noise_est = instantiate(template.noise_est, image_shape,
+                                      template.clean_parameters.border)
+        self._clean = instantiate(template.clean, image_parameters)
+        self._scale = instantiate(template.scale, image_shape)
+        self._add_image = instantiate(template.add_image, image_shape)
+        # thresholds are set by apply_primary_beam()
+        self._apply_primary_beam_model = instantiate(
+            template.apply_primary_beam, image_shape, 0.0, 0.0)
+        self._apply_primary_beam_dirty = instantiate(
+            template.apply_primary_beam, image_shape, 0.0, np.nan)
+
+        def upload_taper(kernel):
+            taper = accel.DeviceArray(context, (pixels,), dtype)
+            host = taper.empty_like()
+            kernel.taper(pixels, host)
+            taper.set(command_queue, host)
+            return taper
+
+        self._grid_to_image.bind(kernel1d=upload_taper(self._gridder.convolve_kernel))
+        self._image_to_grid = None
+        if degrid:
+            self._predict = instantiate(template.degridder, template.array_parameters,
+                                        image_parameters, grid_parameters, max_vis)
+            self._image_to_grid = template.grid_image.instantiate_image_to_grid(
+                command_queue, self._predict.slots['grid'].shape, lm_scale, lm_bias, fft_plan,
+                allocator)
+            self._image_to_grid.bind(kernel1d=upload_taper(self._predict.convolve_kernel))
+        else:
+            max_components = min(pixels**2, (major - 1) * template.clean_parameters.minor)
+            self._predict = instantiate(template.predict, image_parameters, grid_parameters,
+                                        max_vis, max_components)
+        self._model_components = {}
+
+        operations = [
+            ('weights', self._weights),
+            ('gridder', self._gridder),
+            ('predict', self._predict),
+            ('continuum_predict', self._continuum_predict),
+            ('grid_to_image', self._grid_to_image),
+            ('psf_patch', self._psf_patch),
+            ('noise_est', self._noise_est),
+            ('clean', self._clean),
+            ('scale', self._scale),
+            ('add_image', self._add_image),
+            ('apply_primary_beam_model', self._apply_primary_beam_model),
+            ('apply_primary_beam_dirty', self._apply_primary_beam_dirty)
+        ]
+        compounds = {name: list(members) for name, members in _SHARED_SLOTS.items()}
+        if self._weights.template.grid_weights is None:
+            # natural weighting: the weights operation has no uv / weights slots
+            compounds['weights'].remove('weights:weights')
+            compounds['uv'].remove('weights:uv')
+        if degrid:
+            operations.append(('image_to_grid', self._image_to_grid))
+            compounds['degrid'] = ['predict:grid', 'image_to_grid:grid']
+            compounds['layer'].append('image_to_grid:layer')
+            compounds['model'].append('image_to_grid:image')
+        super().__init__(command_queue, operations, compounds, allocator=allocator)
+        # dirty_to_psf swaps the two buffers, so their padding must be interchangeable
+        for a, b in zip(self.slots['dirty'].dimensions, self.slots['psf'].dimensions):
+            a.link(b)
+        self.host_buffer = {name: _Staging(context, self.slots[name])
+                            for name in ('weights', 'uv', 'w_plane', 'vis') if name in self.slots}
+
+    def __call__(self, **kwargs):
+        raise NotImplementedError()
+
+    # ------------------------------------------------------------------ visibilities
+    @property
+    def num_vis(self):
+        return self._gridder.num_vis
+
+    @num_vis.setter
+    def num_vis(self, value):
+        self._gridder.num_vis = value
+        self._predict.num_vis = value
+        self._continuum_predict.num_vis = value
+
+    def _set_buffer(self, name, N, data, extra_index=()):
+        """Stage `data` (N rows) in pinned memory and start its upload."""
+        if len(data) != N:
+            raise ValueError('Lengths do not match')
+        staging = self.host_buffer[name]
+        staging.wait()
+        index = (np.s_[:N],) + extra_index
+        staging.array[index] = data
+        self.buffer(name).set_region(self.command_queue, staging.array, index, index,
+                                     blocking=False)
+        staging.transfer_event = self.command_queue.enqueue_marker()
+
+    @profile_function()
+    def set_coordinates(self, coords):
+        """Upload UVW coordinates from a record array with fields ``uv``, ``sub_uv``
+        (adjacent int16 pairs) and ``w_plane``."""
+        self._set_buffer('uv', self.num_vis, _uv_view(coords))
+        self._set_buffer('w_plane', self.num_vis, coords['w_plane'])
+
+    @profile_function()
+    def set_vis(self, vis):
+        self._set_buffer('vis', self.num_vis, vis)
+
+    @profile_function()
+    def set_weights(self, weights):
+        """Set statistical weights for prediction"""
+        self._set_buffer('weights', self.num_vis, weights)
+
+    # ----------------------------------------------------------------------- weights
+    @profile_function()
+    def clear_weights(self):
+        self._weights.clear()
+
+    @profile_function()
+    def grid_weights(self, uv, weights):
+        self._set_buffer('uv', len(uv), uv, (np.s_[:2],))
+        self._set_buffer('weights', len(uv), weights)
+        self._weights.grid(len(uv))
+
+    @profile_function()
+    def finalize_weights(self):
+        return self._weights.finalize()
+
+    # ------------------------------------------------------------ gridding / prediction
+    def _zero(self, name):
+        with profile_device(self.command_queue, 'clear_' + name):
+            self.buffer(name).zero(self.command_queue)
+
+    @profile_function()
+    def clear_grid(self):
+        self._zero('grid')
+
+    @profile_function()
+    def clear_dirty(self):
+        self._zero('dirty')
+
+    @profile_function()
+    def clear_model(self):
+        self._zero('model')
+        self._model_components.clear()
+
+    @profile_function()
+    def grid(self):
+        self._gridder()
+
+    @profile_function()
+    def predict(self, w):
+        if not self.template.fixed_grid_parameters.degrid:
+            self._predict.set_w(w)
+        self._predict()
+
+    @profile_function()
+    def continuum_predict(self, w):
+        self._continuum_predict.set_w(w)
+        self._continuum_predict()
+
+    def set_sky_model(self, sky_model, phase_centre):
+        self._continuum_predict.set_sky_model(sky_model, phase_centre)
+
+    @profile_function()
+    def grid_to_image(self, w):
+        self._grid_to_image.set_w(w)
+        self._grid_to_image()
+
+    @profile_function()
+    def model_to_grid(self, w):
+        if self._image_to_grid is None:
+            raise RuntimeError('Can only use model_to_grid with degridding')
+        self._image_to_grid.set_w(w)
+        self._image_to_grid()
+
+    @profile_function()
+    def model_to_predict(self):
+        if self.template.fixed_grid_parameters.degrid:
+            raise RuntimeError('Can only use model_to_predict with direct prediction')
+        self._predict.set_sky_image(self._model_components)
+
+    # ------------------------------------------------------------------ image domain
+    @profile_function()
+    def scale_dirty(self, scale_factor):
+        self._scale.set_scale_factor(scale_factor)
+        self._scale()
+
+    @profile_function()
+    def add_model_to_dirty(self):
+        self._add_image()
+
+    @profile_function()
+    def apply_primary_beam(self, threshold):
+        """Applies primary beam power to both model and dirty images."""
+        for op in (self._apply_primary_beam_model, self._apply_primary_beam_dirty):
+            op.threshold = threshold
+            op()
+
+    @profile_function()
+    def dirty_to_psf(self):
+        """Make the current dirty image the PSF by exchanging the two buffers."""
+        dirty = self.buffer('dirty')
+        psf = self.buffer('psf')
+        self.bind(dirty=psf, psf=dirty)
+
+    @profile_function()
+    def psf_patch(self):
+        params = self.template.clean_parameters
+        return self._psf_patch(params.psf_cutoff, params.psf_limit)
+
+    @profile_function()
+    def noise_est(self):
+        return self._noise_est()
+
+    # -------------------------------------------------------------------------- CLEAN
+    @profile_function()
+    def clean_reset(self):
+        self._clean.reset()
+
+    def _record_component(self, pos, pixel):
+        if pos in self._model_components:
+            self._model_components[pos] = self._model_components[pos] + pixel
+        else:
+            self._model_components[pos] = pixel
+
+    @profile_function()
+    def clean_cycle(self, psf_patch, threshold=0.0):
+        peak_value, peak_pos, model_pixel = self._clean(psf_patch, threshold)
+        if peak_pos is not None:
+            self._record_component(peak_pos, model_pixel)
+        return peak_value
+
+    @profile_function()
+    def clean_cycles(self, psf_patch, threshold=0.0, max_cycles=1):
+        """Run up to `max_cycles` minor cycles without leaving the device.
+
+        Equivalent to calling :meth:`clean_cycle` until it returns ``None`` or
+        `max_cycles` calls have been made; returns ``(peak values, stopped)``.
+        """
+        components, stopped = self._clean.run_cycles(psf_patch, threshold, max_cycles)
+        for record in components:
+            self._record_component((int(record['pos'][0]), int(record['pos'][1])),
+                                   np.array(record['pixel']))
+        return components['value'], stopped
+
+    # ------------------------------------------------------------------------ buffers
+    @profile_function(labels=['name'])
+    def get_buffer(self, name):
+        """Get the contents of a buffer as a numpy array."""
+        return self.buffer(name).get(self.command_queue)
+
+    @profile_function(labels=['name'])
+    def set_buffer(self, name, data):
+        """Copy a numpy array to a buffer (blocking)."""
+        self.buffer(name).set(self.command_queue, data)
+
+    def free_buffer(self, name):
+        """Release the device memory of a buffer that is no longer needed."""
+        if name in self.slots:
+            self.slots[name].bind(None)

@@ -1,0 +1,196 @@
+"""FFT-stage and image-arithmetic kernels: the reference's unit tests
+(reference katsdpimager/test/test_image.py) and golden vectors from GridToImageHost /
+ImageToGridHost."""
+import math
+
+import numpy as np
+import pytest
+
+from katsdpimager_b200 import accel, image
+from tests import cases
+from tests.cases import RandomState, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_layer_to_image(gpu):
+    """reference test_image.py TestLayerToImage (rtol 1e-4)."""
+    context, queue = gpu
+    slices, size = 3, 102
+    shape = (slices, size, size)
+    lm_scale = 0.1 / size
+    lm_bias = -lm_scale * size / 3
+    w = 12.3
+    fn = image.LayerToImageTemplate(context, np.float32).instantiate(queue, shape, lm_scale, lm_bias)
+    fn.set_w(w)
+    fn.set_polarization(1)
+    fn.ensure_all_bound()
+    rs = RandomState(1)
+    src = rs.complex_uniform(10.0, 100.0, shape[1:]).astype(np.complex64)
+    kernel1d = rs.uniform(1.0, 2.0, size).astype(np.float32)
+    fn.buffer('kernel1d').set(queue, kernel1d)
+    fn.buffer('layer').set(queue, src)
+    fn.buffer('image').zero(queue)
+    lm = np.arange(size) * lm_scale + lm_bias
+    lm2 = lm * lm
+    n = np.sqrt(1 - lm2[np.newaxis, :, np.newaxis] - lm2[np.newaxis, np.newaxis, :])
+    corrected = np.fft.fftshift(src) * np.exp(2j * math.pi * w * (n - 1))
+    expected = np.zeros(shape, np.float32)
+    expected[1] = corrected.real * n / np.outer(kernel1d, kernel1d)[np.newaxis, ...]
+    fn()
+    np.testing.assert_allclose(expected, fn.buffer('image').get(queue), 1e-4)
+    # accumulates
+    fn()
+    np.testing.assert_allclose(2 * expected, fn.buffer('image').get(queue), 1e-4)
+    with pytest.raises(IndexError):
+        fn.set_polarization(3)
+    with pytest.raises(ValueError):
+        image.LayerToImageTemplate(context, np.float32).instantiate(queue, (1, 101, 101), 1, 0)
+
+
+def test_image_to_layer_roundtrip(gpu):
+    """reference test_image.py TestImageToLayer."""
+    context, queue = gpu
+    slices, size = 3, 102
+    shape = (slices, size, size)
+    lm_scale = 0.1 / size
+    lm_bias = -lm_scale * size / 3
+    w = 12.3
+    i2l = image.ImageToLayerTemplate(context, np.float32).instantiate(queue, shape, lm_scale, lm_bias)
+    i2l.ensure_all_bound()
+    i2l.set_w(w)
+    l2i = image.LayerToImageTemplate(context, np.float32).instantiate(queue, shape, lm_scale, lm_bias)
+    l2i.set_w(w)
+    l2i.bind(image=i2l.buffer('image'), layer=i2l.buffer('layer'), kernel1d=i2l.buffer('kernel1d'))
+    rs = np.random.RandomState(1)
+    expected = rs.uniform(10.0, 100.0, shape).astype(np.float32)
+    kernel1d = rs.uniform(1.0, 2.0, size).astype(np.float32)
+    kernel = np.outer(kernel1d, kernel1d)[np.newaxis, ...]
+    i2l.buffer('image').set(queue, expected * kernel)
+    i2l.buffer('kernel1d').set(queue, kernel1d)
+    i2l.set_polarization(1)
+    i2l()
+    i2l.buffer('image').zero(queue)
+    l2i.set_polarization(1)
+    l2i()
+    actual = l2i.buffer('image').get(queue) * kernel
+    np.testing.assert_allclose(expected[1], actual[1], 1e-4)
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_grid_to_image_and_back(gpu, oracle, dtype):
+    """GridToImage / ImageToGrid against the reference's host classes (golden) and the
+    oracle.  Bar: 1e-4 RMS relative to peak (north_star); observed ~1e-7."""
+    context, queue = gpu
+    fx = cases.image_case()
+    golden = load_golden('image_small')
+    cdtype = np.complex64 if dtype == np.float32 else np.complex128
+    pols, pixels, _ = fx['grid'].shape
+    size = fx['grid_size']
+    template = image.GridImageTemplate(context, dtype)
+    plan = template.make_fft_plan((pixels, pixels), (pixels, pixels))
+    g2i = template.instantiate_grid_to_image(queue, (pols, size, size), fx['lm_scale'],
+                                             fx['lm_bias'], plan)
+    g2i.ensure_all_bound()
+    g2i.buffer('grid').set(queue, np.ascontiguousarray(
+        cases.middle(fx['grid'], (pols, size, size)).astype(cdtype)))
+    g2i.buffer('kernel1d').set(queue, fx['kernel1d'].astype(dtype))
+    g2i.buffer('image').zero(queue)
+    g2i.set_w(fx['w'])
+    g2i()
+    actual = g2i.buffer('image').get(queue)
+    rms = np.sqrt(np.mean((actual - golden['image']) ** 2)) / np.abs(golden['image']).max()
+    assert rms < (1e-6 if dtype == np.float32 else 3e-7)
+    i2g = template.instantiate_image_to_grid(queue, (pols, size, size), fx['lm_scale'],
+                                             fx['lm_bias'], plan)
+    i2g.bind(layer=g2i.buffer('layer'), kernel1d=g2i.buffer('kernel1d'))
+    i2g.ensure_all_bound()
+    i2g.buffer('image').set(queue, fx['model'].astype(dtype))
+    i2g.set_w(fx['w'])
+    i2g()
+    back = i2g.buffer('grid').get(queue)
+    expected = cases.middle(golden['grid_from_model'], back.shape)
+    rms = np.sqrt(np.mean(np.abs(back - expected) ** 2)) / np.abs(expected).max()
+    assert rms < 1e-6
+
+
+def test_grid_to_image_w_precision(gpu, oracle):
+    """Large W phases (thousands of turns) keep parity with the host computation."""
+    context, queue = gpu
+    fx = cases.image_case(pixels=128, grid_size=80, pols=1)
+    pixels = 128
+    template = image.GridImageTemplate(context, np.float32)
+    plan = template.make_fft_plan((pixels, pixels), (pixels, pixels))
+    g2i = template.instantiate_grid_to_image(queue, (1, 80, 80), fx['lm_scale'], fx['lm_bias'], plan)
+    g2i.ensure_all_bound()
+    crop = np.ascontiguousarray(cases.middle(fx['grid'], (1, 80, 80)))
+    g2i.buffer('grid').set(queue, crop)
+    g2i.buffer('kernel1d').set(queue, fx['kernel1d'])
+    w = np.float64(31234.56)
+    g2i.buffer('image').zero(queue)
+    g2i.set_w(w)
+    g2i()
+    expected = np.zeros((1, pixels, pixels), np.float32)
+    oracle.grid_to_image(crop, expected, fx['kernel1d'], fx['lm_scale'], fx['lm_bias'], w)
+    actual = g2i.buffer('image').get(queue)
+    rms = np.sqrt(np.mean((actual - expected) ** 2)) / np.abs(expected).max()
+    assert rms < 1e-5
+
+
+def test_scale(gpu):
+    context, queue = gpu
+    shape = (4, 123, 234)
+    rs = np.random.RandomState(1)
+    fn = image.ScaleTemplate(context, np.float32, shape[0]).instantiate(queue, shape)
+    fn.ensure_all_bound()
+    src = rs.uniform(size=shape).astype(np.float32)
+    scale_factor = np.array([1.2, 2.3, 3.4, -4.5], np.float32)
+    fn.buffer('data').set(queue, src)
+    fn.set_scale_factor(scale_factor)
+    fn()
+    np.testing.assert_allclose(src * scale_factor[:, np.newaxis, np.newaxis],
+                               fn.buffer('data').get(queue))
+    with pytest.raises(ValueError):
+        image.ScaleTemplate(context, np.float32, 4).instantiate(queue, (3, 8, 8))
+
+
+def test_add_image_different_padding(gpu):
+    """reference test_image.py TestAddImage: src and dest padded differently."""
+    context, queue = gpu
+    shape = (4, 123, 234)
+    rs = np.random.RandomState(1)
+    fn = image.AddImageTemplate(context, np.float32, shape[0]).instantiate(queue, shape)
+    for slot, padded in ((fn.slots['src'], (4, 128, 256)), (fn.slots['dest'], (4, 135, 240))):
+        for i, size in enumerate(padded):
+            slot.dimensions[i].link(accel.Dimension(slot.shape[i], min_padded_size=size))
+    fn.ensure_all_bound()
+    assert fn.buffer('src').padded_shape == (4, 128, 256)
+    assert fn.buffer('dest').padded_shape == (4, 135, 240)
+    src_host = rs.uniform(size=shape).astype(np.float32)
+    dest_host = rs.uniform(size=shape).astype(np.float32)
+    fn.buffer('src').set(queue, src_host)
+    fn.buffer('dest').set(queue, dest_host)
+    fn()
+    np.testing.assert_allclose(src_host + dest_host, fn.buffer('dest').get(queue))
+
+
+def test_apply_primary_beam(gpu):
+    context, queue = gpu
+    shape = (4, 123, 234)
+    rs = np.random.RandomState(1)
+    fn = image.ApplyPrimaryBeamTemplate(context, np.float32, shape[0]).instantiate(
+        queue, shape, 0.2, 12345.0)
+    fn.ensure_all_bound()
+    src = rs.uniform(size=shape).astype(np.float32)
+    beam = rs.uniform(size=shape[1:]).astype(np.float32)
+    fn.buffer('data').set(queue, src)
+    fn.buffer('beam_power').set(queue, beam)
+    fn()
+    np.testing.assert_allclose(np.where(beam < 0.2, 12345.0, src / beam),
+                               fn.buffer('data').get(queue))
+    # NaN replacement as used for the dirty image (imaging.py:130-131)
+    fn.replacement = np.nan
+    fn.buffer('data').set(queue, src)
+    fn()
+    out = fn.buffer('data').get(queue)
+    assert np.all(np.isnan(out[:, beam < 0.2])) and not np.any(np.isnan(out[:, beam >= 0.2]))

@@ -1,0 +1,77 @@
+"""End to end: the Imaging facade replaying frontend.process_channel's call sequence
+against the reference's ImagingHost (golden, tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from katsdpimager_b200 import imaging, parameters as prm, weight
+from tests import cases
+from tests.cases import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _rms_rel(actual, expected):
+    return np.sqrt(np.mean((actual - expected) ** 2)) / np.abs(expected).max()
+
+
+@pytest.mark.parametrize('clean_batch', [None, 16])
+def test_imaging_against_host(gpu, clean_batch):
+    context, queue = gpu
+    fx = cases.imaging_case()
+    golden = load_golden('imaging_small')
+    ip, gp, cp = fx['image_parameters'], fx['grid_parameters'], fx['clean_parameters']
+    wp = prm.WeightParameters(weight.WeightType.UNIFORM)
+    template = imaging.ImagingTemplate(context, fx['array_parameters'], ip.fixed, wp, gp.fixed, cp)
+
+    def make():
+        return template.instantiate(queue, ip, gp, fx['vis_block'], 0, fx['major'])
+
+    out = cases.run_imaging(make, fx, clean_batch=clean_batch)
+    np.testing.assert_allclose(out['weights_rms'], golden['weights_rms'], rtol=1e-5)
+    np.testing.assert_allclose(out['psf_peak'], golden['psf_peak'], rtol=1e-5)
+    np.testing.assert_array_equal(out['psf_patch'], golden['psf_patch'])
+    # north_star gates: images within 1e-4 RMS relative to peak
+    assert _rms_rel(out['psf'], golden['psf']) < 1e-5
+    assert _rms_rel(out['dirty0'], golden['dirty0']) < 1e-5
+    np.testing.assert_allclose(out['noise'], golden['noise'], rtol=1e-4)
+    # CLEAN: same number of cycles, same component pixels (bit-exact indices), fluxes 1e-5
+    assert len(out['values']) == len(golden['values'])
+    np.testing.assert_allclose(out['values'], golden['values'], rtol=2e-4)
+    np.testing.assert_array_equal(np.argwhere(out['model'] != 0), np.argwhere(golden['model'] != 0))
+    np.testing.assert_allclose(out['model'], golden['model'],
+                               rtol=0, atol=1e-5 * np.abs(golden['model']).max())
+    assert _rms_rel(out['residual'], golden['residual']) < 1e-4
+    # our component dictionary is keyed by the true positions
+    model = np.zeros_like(out['model'])
+    for pos, flux in zip(out['component_pos'], out['component_flux']):
+        model[:, pos[0], pos[1]] += flux
+    np.testing.assert_allclose(model, out['model'], rtol=1e-6)
+
+
+def test_buffer_management(gpu):
+    context, queue = gpu
+    fx = cases.imaging_case(num_baselines=10, num_dumps=5)
+    ip, gp, cp = fx['image_parameters'], fx['grid_parameters'], fx['clean_parameters']
+    wp = prm.WeightParameters(weight.WeightType.NATURAL)
+    template = imaging.ImagingTemplate(context, fx['array_parameters'], ip.fixed, wp, gp.fixed, cp)
+    imager = template.instantiate(queue, ip, gp, 256, 0, 2)
+    imager.ensure_all_bound()
+    # dirty_to_psf swaps the two buffers (imaging.py:370-373)
+    dirty, psf = imager.buffer('dirty'), imager.buffer('psf')
+    imager.dirty_to_psf()
+    assert imager.buffer('dirty') is psf and imager.buffer('psf') is dirty
+    assert imager._clean.buffer('dirty') is psf
+    # shared slots really share memory
+    assert imager._gridder.buffer('grid') is imager._grid_to_image.buffer('grid')
+    assert imager._predict.buffer('grid') is imager._image_to_grid.buffer('grid')
+    assert imager._gridder.buffer('weights_grid') is imager._weights.buffer('grid')
+    imager.free_buffer('layer')
+    assert imager.buffer('layer') is None
+    imager.clear_weights()
+    assert imager.finalize_weights() == (None, 1.0)
+    assert np.all(imager.get_buffer('weights_grid') == 1.0)
+    with pytest.raises(ValueError):
+        imager.num_vis = 257
+    imager.num_vis = 3
+    with pytest.raises(ValueError):
+        imager.set_vis(np.zeros((4, 2), np.complex64))

@@ -1,0 +1,214 @@
+"""The CPU oracle against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  These pin the oracle; the GPU tests then compare the
+CUDA path with the oracle and with the same golden vectors."""
+import numpy as np
+import pytest
+
+from tests import cases
+from tests.cases import load_golden
+
+
+def test_expj2pi(oracle):
+    x = np.linspace(-20.3, 17.9, 1001)
+    np.testing.assert_allclose(oracle.expj2pi(x), np.exp(2j * np.pi * x), atol=1e-13)
+    x32 = x.astype(np.float32)
+    assert oracle.expj2pi(x32).dtype == np.complex64
+
+
+@pytest.mark.parametrize('name', ['test_grid', 'meerkat_k7'])
+def test_convolution_kernel(oracle, name):
+    ip, gp = cases.lut_cases()[name]
+    golden = load_golden('lut_' + name)
+    lut = oracle.convolution_kernel(ip, gp)
+    assert lut.shape == golden['data'].shape
+    np.testing.assert_allclose(lut, golden['data'], rtol=0, atol=2e-7)
+    np.testing.assert_allclose(oracle.taper(gp, ip.pixels), golden['taper'], rtol=1e-12)
+
+
+def test_grid_reference_fixture(oracle):
+    """GridderHost / DegridderHost outputs on the reference's own unit-test inputs."""
+    fx = cases.reference_grid_fixture()
+    golden = load_golden('grid_reference_fixture')
+    ip, gp = fx['image_parameters'], fx['grid_parameters']
+    lut = oracle.convolution_kernel(ip, gp)
+    values = np.zeros((4, ip.pixels, ip.pixels), np.complex128)
+    wgrid = np.zeros(values.shape, np.float32)
+    cases.middle(wgrid, fx['weights_grid'].shape)[:] = fx['weights_grid']
+    oracle.grid(lut, values, wgrid, fx['uv'], fx['sub_uv'], fx['w_plane'], fx['vis'])
+    np.testing.assert_allclose(values[:, ::3, :], golden['grid_rows'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(values.sum(axis=(1, 2)), golden['grid_sum'], rtol=1e-9)
+    residual = fx['degrid_vis'].copy()
+    oracle.degrid(lut, np.ascontiguousarray(fx['degrid_grid']), fx['uv'], fx['sub_uv'],
+                  fx['w_plane'], fx['degrid_weights'], residual)
+    np.testing.assert_allclose(residual, golden['residual'], rtol=1e-6, atol=1e-6)
+
+
+def test_grid_reference_first_principles(oracle):
+    """The expected-value computation of reference test_grid.py:91-112 (numpy, double)."""
+    fx = cases.reference_grid_fixture()
+    ip, gp = fx['image_parameters'], fx['grid_parameters']
+    lut = oracle.convolution_kernel(ip, gp)
+    pixels = ip.pixels
+    actual = np.zeros((4, pixels, pixels), np.complex128)
+    wgrid = np.zeros(actual.shape, np.float32)
+    cases.middle(wgrid, fx['weights_grid'].shape)[:] = fx['weights_grid']
+    oracle.grid(lut, actual, wgrid, fx['uv'], fx['sub_uv'], fx['w_plane'], fx['vis'])
+    expected = np.zeros_like(actual)
+    uv_bias = (lut.shape[-1] - 1) // 2 - pixels // 2
+    wshape = fx['weights_grid'].shape
+    for i in range(len(fx['uv'])):
+        kernel = np.conj(np.outer(lut[fx['w_plane'][i], fx['sub_uv'][i, 1], :],
+                                  lut[fx['w_plane'][i], fx['sub_uv'][i, 0], :]))
+        u = fx['uv'][i, 0] - uv_bias
+        v = fx['uv'][i, 1] - uv_bias
+        wu = fx['uv'][i, 0] + wshape[2] // 2
+        wv = fx['uv'][i, 1] + wshape[1] // 2
+        for j in range(4):
+            expected[j, v:v + kernel.shape[0], u:u + kernel.shape[1]] += \
+                fx['vis'][i, j].astype(np.complex128) * fx['weights_grid'][j, wv, wu] * kernel
+    np.testing.assert_allclose(expected, actual, 1e-5, 1e-8)
+
+
+def test_grid_small(oracle):
+    fx = cases.small_grid_case()
+    golden = load_golden('grid_small')
+    lut = oracle.convolution_kernel(fx['image_parameters'], fx['grid_parameters'])
+    values = np.zeros(golden['grid'].shape, np.complex64)
+    oracle.grid(lut, values, fx['weights_grid'], fx['uv'], fx['sub_uv'], fx['w_plane'], fx['vis'])
+    scale = np.abs(golden['grid']).max()
+    np.testing.assert_allclose(values, golden['grid'], rtol=0, atol=2e-6 * scale)
+    residual = fx['vis'].copy()
+    oracle.degrid(lut, golden['grid'], fx['uv'], fx['sub_uv'], fx['w_plane'], fx['weights'],
+                  residual)
+    np.testing.assert_allclose(residual, golden['residual'], rtol=0,
+                               atol=2e-6 * np.abs(golden['residual']).max())
+
+
+def test_image(oracle):
+    fx = cases.image_case()
+    golden = load_golden('image_small')
+    image = np.zeros(fx['grid'].shape, np.float32)
+    oracle.grid_to_image(fx['grid'], image, fx['kernel1d'], fx['lm_scale'], fx['lm_bias'], fx['w'])
+    np.testing.assert_allclose(image, golden['image'], rtol=0,
+                               atol=1e-6 * np.abs(golden['image']).max())
+    # cropped (device-style) grid gives the same image
+    size = fx['grid_size']
+    crop = np.ascontiguousarray(cases.middle(fx['grid'], (2, size, size)))
+    image2 = np.zeros_like(image)
+    oracle.grid_to_image(crop, image2, fx['kernel1d'], fx['lm_scale'], fx['lm_bias'], fx['w'])
+    np.testing.assert_array_equal(image, image2)
+    back = oracle.image_to_grid(fx['model'], fx['kernel1d'], fx['lm_scale'], fx['lm_bias'], fx['w'])
+    np.testing.assert_allclose(back, golden['grid_from_model'], rtol=0,
+                               atol=1e-6 * np.abs(golden['grid_from_model']).max())
+
+
+@pytest.mark.parametrize('name', ['clean_i', 'clean_sumsq'])
+def test_clean(oracle, name):
+    """Bit-exact CLEAN: component positions, values, fluxes, tiles and residual."""
+    fx = cases.clean_case(name)
+    golden = load_golden(name)
+    cp = fx['clean_parameters']
+    assert oracle.psf_patch(fx['psf'], cp.psf_cutoff, cp.psf_limit) == tuple(golden['patch'])
+    assert oracle.noise_est(fx['dirty'], cp.border) == golden['noise']
+    dirty = fx['dirty'].copy()
+    model = np.zeros_like(dirty)
+    cleaner = oracle.CleanHost(fx['image_parameters'].pixels, cp.border, cp.mode, cp.loop_gain,
+                               dirty, fx['psf'], model)
+    cleaner.reset()
+    np.testing.assert_array_equal(cleaner.tile_max, golden['tile_max0'])
+    np.testing.assert_array_equal(cleaner.tile_pos, golden['tile_pos0'])
+    values, positions, reported, pixels = [], [], [], []
+    for _ in range(fx['cycles']):
+        value, pos, pixel = cleaner(fx['psf_patch'], fx['threshold'])
+        if value is None:
+            break
+        values.append(value)
+        positions.append(pos)
+        reported.append(cleaner.reported_pos)
+        pixels.append(pixel)
+    assert len(values) == len(golden['values'])
+    assert len(values) < fx['cycles']       # the threshold, not the cycle limit, ended it
+    # The reference returns a position aliased to the tile's new peak (oracle.c
+    # kor_clean_cycle); the true component positions are pinned through the model image.
+    np.testing.assert_array_equal(np.array(reported, np.int32), golden['positions'])
+    assert np.any(np.array(reported) != np.array(positions))
+    expected_model = np.zeros_like(model)
+    for pos, pixel in zip(positions, pixels):
+        expected_model[:, pos[0], pos[1]] += pixel
+    np.testing.assert_array_equal(model, expected_model)
+    np.testing.assert_array_equal(model, golden['model'])
+    np.testing.assert_array_equal(np.array(values, np.float32), golden['values'])
+    np.testing.assert_array_equal(np.array(pixels, np.float32), golden['pixels'])
+    np.testing.assert_array_equal(cleaner.tile_max, golden['tile_max'])
+    np.testing.assert_array_equal(cleaner.tile_pos, golden['tile_pos'])
+    np.testing.assert_array_equal(dirty, golden['residual'])
+
+
+def test_psf_patch_known_answers(oracle):
+    """Known answers of reference test_clean.py:11-37."""
+    def fresh():
+        psf = np.zeros((4, 206, 304), np.float32)
+        psf[:, 103, 152] = 1.0
+        return psf
+    assert oracle.psf_patch(fresh(), 0.01) == (4, 1, 1)
+    psf = fresh()
+    psf[0, 0, 0] = 0.1
+    assert oracle.psf_patch(psf, 0.01) == (4, 206, 304)
+    psf = fresh()
+    psf[3, 205, 303] = -0.2
+    assert oracle.psf_patch(psf, 0.01) == (4, 205, 303)
+    psf = fresh()
+    psf[0, 0, 0] = 0.4
+    psf[3, 205, 303] = 0.3
+    psf[1, 110, 150] = 0.2
+    assert oracle.psf_patch(psf, 0.01, limit=50 / 206) == (4, 15, 5)
+
+
+@pytest.mark.parametrize('name', ['uniform', 'robust', 'natural'])
+def test_weights(oracle, name):
+    fx = cases.weights_case()
+    golden = load_golden('weights_' + name)
+    wgrid = np.zeros(fx['shape'], np.float32)
+    weights = oracle.WeightsHost({'natural': 0, 'uniform': 1, 'robust': 2}[name], wgrid)
+    weights.robustness = fx['robustness']
+    weights.clear()
+    uv = fx['uv'].copy()
+    weights.grid(uv, fx['weights'])
+    np.testing.assert_array_equal(uv, fx['uv'])
+    rms, normalized_rms = weights.finalize()
+    np.testing.assert_allclose(wgrid, golden['grid'], rtol=1e-6)
+    if name == 'natural':
+        assert rms is None and normalized_rms == 1.0
+    else:
+        np.testing.assert_allclose(rms, golden['rms'], rtol=1e-6)
+        np.testing.assert_allclose(normalized_rms, golden['normalized_rms'], rtol=1e-6)
+
+
+def test_weights_known_answers(oracle):
+    """Known answers of reference test_weight.py:10-57."""
+    uv = np.array([[-10, 5], [23, 17], [-10, 5], [-10, 5], [-10, 6], [-11, 5]], np.int16)
+    w = np.array([[1, 10, 100, 1000], [2, 20, 200, 2000], [4, 40, 400, 4000],
+                  [8, 80, 800, 8000], [16, 160, 1600, 16000], [32, 320, 3200, 32000]], np.float32)
+    wgrid = np.zeros((4, 100, 200), np.float32)
+    oracle.WeightsHost(1, wgrid).grid(uv, w)
+    expected = np.zeros_like(wgrid)
+    for i in range(4):
+        expected[i, 55, 90] = 13 * 10**i
+        expected[i, 67, 123] = 2 * 10**i
+        expected[i, 56, 90] = 16 * 10**i
+        expected[i, 55, 89] = 32 * 10**i
+    np.testing.assert_array_equal(wgrid, expected)
+
+
+def test_predict(oracle):
+    fx = cases.predict_case()
+    golden = load_golden('predict_small')
+    np.testing.assert_allclose(
+        oracle.uvw_scale_bias(fx['image_parameters'], fx['grid_parameters']),
+        golden['scale_bias'], rtol=1e-12)
+    vis = fx['vis'].copy()
+    oracle.predict(vis, fx['uv'], fx['sub_uv'], fx['w_plane'], fx['weights'], fx['lmn'],
+                   fx['flux'], fx['oversample'], fx['uv_scale'], fx['w_scale'], fx['w_bias'])
+    # single-precision phases of hundreds of turns: the reference's own tolerance for
+    # this routine is rtol 5e-4 (test_predict.py:92)
+    np.testing.assert_allclose(vis, golden['residual'], rtol=5e-4, atol=5e-4)
