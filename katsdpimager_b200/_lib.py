@@ -131,9 +131,27 @@ def check(rc):
         raise KibError('{} (code {})'.format(msg.decode('utf-8', 'replace') if msg else 'error', rc))
 
 
+#: entry points that launch exactly one of this library's kernels
+_ONE_KERNEL = frozenset([
+    'kib_grid', 'kib_degrid', 'kib_grid_to_layer', 'kib_layer_to_grid', 'kib_layer_to_image',
+    'kib_image_to_layer', 'kib_scale', 'kib_add_image', 'kib_apply_primary_beam',
+    'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
+    'kib_abs_histogram', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
+    'kib_density_weights', 'kib_fill', 'kib_predict', 'kib_fp32_peak_kernel'])
+
+#: number of hand-written kernels launched through this module (cuFFT and memset/memcpy
+#: are not counted); bench.py reports the difference over its timed region
+kernel_launches = 0
+
+
 def call(name, *args):
     """Invoke entry point `name`, raising :class:`KibError` on failure."""
+    global kernel_launches
     check(getattr(load(), name)(*args))
+    if name in _ONE_KERNEL:
+        kernel_launches += 1
+    elif name == 'kib_clean_minor_cycles':
+        kernel_launches += int(args[26])     # one launch per requested cycle
 
 
 def dtype_code(dtype):

@@ -28,7 +28,8 @@
 namespace kib {
 
 constexpr int GRID_BATCH = 16;          // visibilities staged per group per batch
-constexpr int GRID_MAX_THREADS = 1024;
+constexpr int GRID_MAX_GROUP = 512;      // largest thread group (one visibility stream)
+constexpr int GRID_MAX_GROUPS_PER_BLOCK = 32;
 
 struct GridParams {
     void *grid;
@@ -73,8 +74,8 @@ template <> struct Acc<double> {
     }
 };
 
-template <typename Real, int P, int MX, int MY>
-__global__ void __launch_bounds__(GRID_MAX_THREADS / 4)
+template <typename Real, int P, int MX, int MY, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 grid_kernel(const GridParams prm)
 {
     typedef typename Acc<Real>::type Complex;
@@ -279,7 +280,7 @@ static bool choose_config(int K, int P, int dtype, GridConfig *out)
             if (!config_allowed(mx, my, P, dtype)) continue;
             int tx = (K + mx - 1) / mx;
             int ty = (K + my - 1) / my;
-            if (tx * ty > GRID_MAX_THREADS / 4) continue;
+            if (tx * ty > GRID_MAX_GROUP) continue;
             double waste = (double) (mx * tx) * (my * ty) / ((double) K * K);
             // Loads per cell (mx + my LUT fetches amortised over mx*my cells), and a mild
             // preference for more cells per thread (amortises the record fetch).
@@ -300,12 +301,14 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
     const int group = prm.tx * prm.ty;
     int gpb = 256 / group;
     if (gpb < 1) gpb = 1;
+    if (gpb > GRID_MAX_GROUPS_PER_BLOCK) gpb = GRID_MAX_GROUPS_PER_BLOCK;
     prm.group_size = group;
     prm.groups_per_block = gpb;
     const int threads = gpb * group;
     // Enough groups to fill the machine a few times over, but runs long enough
     // that the final flush (MX*MY*P reds per thread) stays negligible.
-    const long long target_groups = (long long) sm_count() * 4 * (1024 / (threads < 64 ? 64 : threads)) * gpb;
+    const long long blocks_per_sm = 2048 / (threads < 64 ? 64 : threads);
+    const long long target_groups = (long long) sm_count() * 2 * blocks_per_sm * gpb;
     long long run = (prm.num_vis + target_groups - 1) / target_groups;
     if (run < 4 * GRID_BATCH) run = 4 * GRID_BATCH;
     if (run > 8192) run = 8192;
@@ -314,7 +317,10 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
     const long long groups = (prm.num_vis + run - 1) / run;
     const long long blocks = (groups + gpb - 1) / gpb;
     const size_t smem = (size_t) gpb * GRID_BATCH * (sizeof(int4) + sizeof(int) + P * sizeof(float2));
-    grid_kernel<Real, P, MX, MY><<<(unsigned) blocks, threads, smem, stream>>>(prm);
+    if (threads <= 256)
+        grid_kernel<Real, P, MX, MY, 256><<<(unsigned) blocks, threads, smem, stream>>>(prm);
+    else
+        grid_kernel<Real, P, MX, MY, GRID_MAX_GROUP><<<(unsigned) blocks, threads, smem, stream>>>(prm);
     KIB_CHECK_LAUNCH();
     return 0;
 }

@@ -30,9 +30,11 @@ def test_imaging_against_host(gpu, clean_batch):
     np.testing.assert_allclose(out['weights_rms'], golden['weights_rms'], rtol=1e-5)
     np.testing.assert_allclose(out['psf_peak'], golden['psf_peak'], rtol=1e-5)
     np.testing.assert_array_equal(out['psf_patch'], golden['psf_patch'])
-    # north_star gates: images within 1e-4 RMS relative to peak
-    assert _rms_rel(out['psf'], golden['psf']) < 1e-5
-    assert _rms_rel(out['dirty0'], golden['dirty0']) < 1e-5
+    # north_star gate: images within 1e-4 RMS relative to peak.  Observed ~1e-5: single
+    # precision FFT round-off (cuFFT vs pocketfft) amplified by the taper division
+    # towards the image edges, where the taper falls to ~1e-2.
+    assert _rms_rel(out['psf'], golden['psf']) < 1e-4
+    assert _rms_rel(out['dirty0'], golden['dirty0']) < 1e-4
     np.testing.assert_allclose(out['noise'], golden['noise'], rtol=1e-4)
     # CLEAN: same number of cycles, same component pixels (bit-exact indices), fluxes 1e-5
     assert len(out['values']) == len(golden['values'])
