@@ -58,6 +58,8 @@ struct GridParams {
     int group_size;          // TX*TY
     int groups_per_block;
     int run;                 // visibilities per group
+    unsigned magic_x, magic_y;   // floor(2^32 / BX) + 1: exact u % BX for u < 65536
+    int num_units;               // work units (gpb groups x run visibilities each)
 };
 
 template <typename Real> struct Acc;
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(MAXT)
 grid_kernel(const GridParams prm)
 {
     typedef typename Acc<Real>::type Complex;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     // Layout: int4 header[groups][BATCH]; int residues[groups][BATCH]; float2 sample[groups][BATCH][P]
     const int gpb = prm.groups_per_block;
     int4 *hdr_all = reinterpret_cast<int4 *>(smem_raw);
@@ -257,6 +259,466 @@ grid_kernel(const GridParams prm)
     if (rejected != 0 && prm.num_rejected != nullptr) atomicAdd(prm.num_rejected, rejected);
 }
 
+// =====================================================================================
+// Fast path: convolution-kernel table resident in shared memory, visibility records
+// pre-staged by a streaming pass and pulled into shared memory by TMA bulk copies.
+//
+// Used whenever the (rotation-friendly, see below) copy of the table fits in shared
+// memory, which covers the small-support / many-visibility regime (e.g. 7x7 support,
+// 16 W planes: 14 KB).  Differences from the generic kernel above:
+//  * `grid_stage_kernel` (one thread per visibility, fully parallel so the dependent
+//    uv -> density-weight gather latency is hidden by occupancy) writes one compact
+//    record per visibility: footprint origin, shared-memory offsets of its u and v tap
+//    rows, bit masks of the column / row slots that moved to a new grid cell relative to
+//    the previous visibility of the run, and the weighted samples.  Records are laid
+//    out [block][batch][entry][group] so that a block's batch is one contiguous chunk
+//    and the groups sharing a warp read adjacent records (no bank conflicts);
+//  * the gridding kernel streams those chunks through a 3-stage shared-memory ring
+//    with cp.async.bulk + mbarrier, so no thread ever waits on global memory;
+//  * each table row is stored twice back to back with period BX (resp. BY) and zero
+//    padding beyond K, so the tap of column slot s is at  row + (BX - u0 % BX) + s:
+//    no modulo and no bounds test in the inner loop, and slot offsets are per-thread
+//    constants;
+//  * the inner loop runs in warp lock step over consecutive visibilities that keep all
+//    of the warp's cells (loads + FMAs only); when any lane's cell moved, the whole
+//    warp leaves it, the affected lanes flush, and the loop resumes.
+constexpr int GRID_LUT_SMEM_LIMIT = 96 * 1024;    // bytes of shared memory for the table
+constexpr int GRID_STAGES = 3;
+constexpr int GRID_TMA_BATCH = 8;                 // records per group per stage
+
+__host__ __device__ constexpr int grid_record_bytes(int P) { return 16 + (8 * P + 15) / 16 * 16; }
+
+struct GridStageParams {
+    unsigned char *records;
+    const float *weights_grid;
+    const short4 *uv;
+    const short *w_plane;
+    const float2 *vis;
+    int32_t *num_rejected;
+    long long weights_pol_stride;
+    long long num_vis;
+    long long total;             // records to write (num_vis rounded up to whole blocks)
+    int weights_row_stride;
+    int grid_size;
+    int w_planes;
+    int oversample;
+    int kernel_width;
+    int uv_bias;
+    int half_grid;
+    int bx, by;
+    int groups_per_block;
+    int run;
+    int lutv_base;               // offset of the v table in 8-byte units
+    // doubled kernel tables (see grid_tma_kernel), built by the first threads
+    float2 *tables;
+    const float2 *lut;
+    int lut_slice_stride, lut_tap_offset;
+    int lutx_count, luty_count;
+};
+
+__device__ __forceinline__ unsigned change_mask(int old_pos, int new_pos, int B)
+{
+    const int d = new_pos - old_pos;
+    if (d == 0) return 0u;
+    if (d >= B || -d >= B) return ~0u;
+    // d > 0: columns old .. old + d - 1 leave; d < 0: columns new .. new - d - 1 enter
+    // (each takes over the slot of the column B cells away).
+    int start = (d > 0 ? old_pos : new_pos) % B;
+    const int count = d > 0 ? d : -d;
+    unsigned mask = 0;
+    for (int i = 0; i < count; i++) {
+        mask |= 1u << start;
+        if (++start == B) start = 0;
+    }
+    return mask;
+}
+
+template <int P>
+__global__ void __launch_bounds__(256)
+grid_stage_kernel(const GridStageParams prm)
+{
+    constexpr int REC = grid_record_bytes(P);
+    const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = prm.kernel_width, G = prm.grid_size, BX = prm.bx, BY = prm.by;
+    if (idx < prm.lutx_count + prm.luty_count) {
+        // table entry: row r of the u (period BX) or v (period BY) table, stored twice
+        const bool is_v = idx >= prm.lutx_count;
+        const int t = is_v ? (int) idx - prm.lutx_count : (int) idx;
+        const int period = is_v ? BY : BX;
+        const int row = t / (2 * period);
+        int d = t - row * 2 * period;
+        if (d >= period) d -= period;
+        prm.tables[idx] = d < K ? __ldg(prm.lut + (long long) row * prm.lut_slice_stride
+                                        + prm.lut_tap_offset + d)
+                                : make_float2(0.0f, 0.0f);
+    }
+    if (idx >= prm.total) return;
+    // position of this visibility in the [block][batch][entry][group] layout
+    const long long group_id = idx / prm.run;
+    const int r = (int) (idx - group_id * prm.run);
+    const int batch = r / GRID_TMA_BATCH, e = r - batch * GRID_TMA_BATCH;
+    const long long block = group_id / prm.groups_per_block;
+    const int g = (int) (group_id - block * prm.groups_per_block);
+    const int nbatches = prm.run / GRID_TMA_BATCH;
+    const long long slot = (((block * nbatches + batch) * GRID_TMA_BATCH + e)
+                            * prm.groups_per_block + g);
+    unsigned char *rec = prm.records + slot * REC;
+
+    int4 h = make_int4(0, BX | ((prm.lutv_base + BY) << 16), 0, 0);     // null record
+    float2 v[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) v[p] = make_float2(0.0f, 0.0f);
+    if (idx < prm.num_vis) {
+        const short4 c = prm.uv[idx];
+        int w = prm.w_plane[idx];
+        int u0 = c.x - prm.uv_bias, v0 = c.y - prm.uv_bias;
+        int su = c.z, sv = c.w;
+        const bool ok = u0 >= 0 && v0 >= 0 && u0 + K <= G && v0 + K <= G
+                        && w >= 0 && w < prm.w_planes
+                        && su >= 0 && su < prm.oversample && sv >= 0 && sv < prm.oversample;
+        if (!ok) {
+            // contributes nothing; harmless stand-in coordinates (stateless, so that the
+            // next visibility's masks can be derived from them as well)
+            u0 = 0; v0 = 0; w = 0; su = 0; sv = 0;
+            if (prm.num_rejected != nullptr) atomicAdd(prm.num_rejected, 1);
+        }
+        h.x = u0 | (v0 << 16);
+        const int lutu = ((w * prm.oversample + su) * 2 * BX) + BX - u0 % BX;
+        const int lutv = prm.lutv_base + ((w * prm.oversample + sv) * 2 * BY) + BY - v0 % BY;
+        h.y = lutu | (lutv << 16);
+        if (r == 0) {
+            h.z = -1;       // first visibility of a run: every slot is new
+            h.w = -1;
+        } else {
+            const short4 pc = prm.uv[idx - 1];
+            const int pw = prm.w_plane[idx - 1];
+            int pu = pc.x - prm.uv_bias, pv = pc.y - prm.uv_bias;
+            const bool pok = pu >= 0 && pv >= 0 && pu + K <= G && pv + K <= G
+                             && pw >= 0 && pw < prm.w_planes
+                             && pc.z >= 0 && pc.z < prm.oversample
+                             && pc.w >= 0 && pc.w < prm.oversample;
+            if (!pok) { pu = 0; pv = 0; }
+            h.z = (int) change_mask(pu, u0, BX);
+            h.w = (int) change_mask(pv, v0, BY);
+        }
+        if (ok) {
+            const long long waddr = (long long) (c.y + prm.half_grid) * prm.weights_row_stride
+                                    + (c.x + prm.half_grid);
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const float wt = __ldg(prm.weights_grid + p * prm.weights_pol_stride + waddr);
+                v[p] = __ldg(prm.vis + idx * P + p);
+                v[p].x *= wt;
+                v[p].y *= wt;
+            }
+        }
+    }
+    *reinterpret_cast<int4 *>(rec) = h;
+    float2 *out = reinterpret_cast<float2 *>(rec + 16);
+    if (P % 2 == 0) {
+#pragma unroll
+        for (int p = 0; p < P; p += 2)
+            *reinterpret_cast<float4 *>(out + p) = make_float4(v[p].x, v[p].y, v[p + 1].x, v[p + 1].y);
+    } else {
+#pragma unroll
+        for (int p = 0; p < P; p++) out[p] = v[p];
+    }
+}
+
+// ---- mbarrier / bulk-copy helpers (sm_90+ PTX)
+__device__ __forceinline__ unsigned smem_u32(const void *ptr)
+{
+    return (unsigned) __cvta_generic_to_shared(ptr);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes,
+                                              unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename Real, int P, int MX, int MY, int MAXT, int MINB, bool TX1>
+__global__ void __launch_bounds__(MAXT, MINB)
+grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
+                const float2 *__restrict__ tables)
+{
+    typedef typename Acc<Real>::type Complex;
+    constexpr int REC = grid_record_bytes(P);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int gpb = prm.groups_per_block;
+    const int K = prm.kernel_width;
+    const int BX = prm.bx, BY = prm.by;
+    const int G = prm.grid_size;
+    const int rows = prm.w_planes * prm.oversample;
+    // Shared memory: barriers | record ring [STAGES][BATCH][gpb] | u table [rows][2 BX] |
+    // v table [rows][2 BY] (aliases the u table when BX == BY)
+    unsigned long long *const full = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned long long *const empty = full + GRID_STAGES;
+    unsigned long long *const lut_bar = empty + GRID_STAGES;
+    unsigned char *const ring = smem_raw + 128;
+    const int stage_bytes = GRID_TMA_BATCH * gpb * REC;
+    float2 *const lutx = reinterpret_cast<float2 *>(ring + GRID_STAGES * stage_bytes);
+    const int lutx_count = rows * 2 * BX;
+    const int luty_count = BX == BY ? 0 : rows * 2 * BY;
+    float2 *const luty = BX == BY ? lutx : lutx + lutx_count;
+
+    const int tid = threadIdx.x;
+    const unsigned lanes = __activemask();      // a block need not be a whole number of warps
+    const int nbatches = prm.run / GRID_TMA_BATCH;
+    // Persistent blocks: block k walks work units k, k + gridDim.x, ...; a unit is what
+    // `gpb` groups grid in one run (gpb * run visibilities, `nbatches` ring stages).
+    // Virtual batch vb of this block is batch vb % nbatches of its (vb / nbatches)-th unit.
+    const int my_units = prm.num_units > (int) blockIdx.x
+        ? (prm.num_units - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+    const int my_batches = my_units * nbatches;
+    auto chunk_of = [&](int vb) {
+        const int k = vb / nbatches;
+        const long long unit = (long long) blockIdx.x + (long long) k * gridDim.x;
+        return records + (unit * nbatches + (vb - k * nbatches)) * stage_bytes;
+    };
+
+    if (tid == 0) {
+        const unsigned warps = (blockDim.x + 31) / 32;
+        for (int s = 0; s < GRID_STAGES; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, warps);
+        }
+        mbar_init(lut_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned table_bytes = (unsigned) ((lutx_count + luty_count) * sizeof(float2));
+        mbar_expect_tx(lut_bar, table_bytes);
+        bulk_copy_g2s(lutx, tables, table_bytes, lut_bar);
+        for (int s = 0; s < GRID_STAGES && s < my_batches; s++) {
+            mbar_expect_tx(full + s, stage_bytes);
+            bulk_copy_g2s(ring + s * stage_bytes, chunk_of(s), stage_bytes, full + s);
+        }
+    }
+    __syncthreads();        // barriers initialised
+    mbar_wait(lut_bar, 0);  // tables have landed
+
+    const int g = tid / prm.group_size;
+    const int q = tid - g * prm.group_size;
+    const int ty = q / prm.tx;
+    const int tx = q - ty * prm.tx;
+    const unsigned char *const lut_bytes = reinterpret_cast<const unsigned char *>(lutx);
+
+    // Per-thread slot constants
+    int xoff[MX], yoff[MY];
+    unsigned my_xmask = 0, my_ymask = 0;
+#pragma unroll
+    for (int i = 0; i < MX; i++) {
+        const int s = TX1 ? i : tx + i * prm.tx;
+        xoff[i] = s * (int) sizeof(float2);
+        my_xmask |= 1u << s;
+    }
+#pragma unroll
+    for (int j = 0; j < MY; j++) {
+        const int s = ty + j * prm.ty;
+        yoff[j] = s * (int) sizeof(float2);
+        my_ymask |= 1u << s;
+    }
+
+    Complex acc[MY][MX][P];
+#pragma unroll
+    for (int j = 0; j < MY; j++)
+#pragma unroll
+        for (int i = 0; i < MX; i++)
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                acc[j][i][p].x = 0;
+                acc[j][i][p].y = 0;
+            }
+    int pu0 = 0, pv0 = 0;       // footprint origin at this thread's last flush check
+    bool valid = false;
+    Complex *const grid = static_cast<Complex *>(prm.grid);
+
+    // Flush every accumulator selected by the masks to its cell under origin (pu0, pv0).
+    // The reductions sit in branches but only read the accumulators; the zeroing is a
+    // branch-free select so that the accumulators never change registers.
+    auto flush_cells = [&](unsigned xm, unsigned ym) {
+        const int pru = pu0 - BX * (int) __umulhi((unsigned) pu0, prm.magic_x);
+        const int prv = pv0 - BY * (int) __umulhi((unsigned) pv0, prm.magic_y);
+        bool hit[MY][MX];
+#pragma unroll
+        for (int i = 0; i < MX; i++) {
+            const int sx = xoff[i] / (int) sizeof(float2);
+            const bool cx = (xm >> sx) & 1;
+            int dx = sx - pru;
+            if (dx < 0) dx += BX;
+            const int col = pu0 + dx;
+#pragma unroll
+            for (int j = 0; j < MY; j++) {
+                const int sy = yoff[j] / (int) sizeof(float2);
+                hit[j][i] = cx || ((ym >> sy) & 1);
+                if (hit[j][i]) {
+                    int dy = sy - prv;
+                    if (dy < 0) dy += BY;
+                    const int row = pv0 + dy;
+                    if (col < G && row < G) {
+                        Complex *ptr = grid + ((unsigned) row * (unsigned) prm.grid_row_stride
+                                               + (unsigned) col);
+#pragma unroll
+                        for (int p = 0; p < P; p++) {
+                            Acc<Real>::flush(ptr, acc[j][i][p]);
+                            ptr += prm.grid_pol_stride;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MY; j++)
+#pragma unroll
+            for (int i = 0; i < MX; i++)
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    acc[j][i][p].x = hit[j][i] ? (Real) 0 : acc[j][i][p].x;
+                    acc[j][i][p].y = hit[j][i] ? (Real) 0 : acc[j][i][p].y;
+                }
+    };
+
+    const int rec_stride = gpb * REC;       // bytes between consecutive entries of a group
+    for (int b = 0; b < my_batches; b++) {
+        const int stage = b % GRID_STAGES;
+        if (b != 0 && b % nbatches == 0 && valid) {
+            // next work unit: unrelated visibilities, start from clean accumulators
+            flush_cells(~0u, ~0u);
+            valid = false;
+        }
+        mbar_wait(full + stage, (b / GRID_STAGES) & 1);
+        const unsigned char *rec = ring + stage * stage_bytes + g * REC;
+        // ---- process the batch.  The flush lives in the outer loop so that the inner
+        // loop contains nothing but loads and FMAs on the register accumulators.
+        int e = 0;
+#pragma unroll 1
+        while (e < GRID_TMA_BATCH) {
+            int4 h = *reinterpret_cast<const int4 *>(rec);
+            if (((unsigned) h.z & my_xmask) | ((unsigned) h.w & my_ymask)) {
+                if (valid) flush_cells(h.z, h.w);
+                pu0 = h.x & 0xffff;
+                pv0 = (unsigned) h.x >> 16;
+                valid = true;
+            }
+#pragma unroll 1
+            for (;;) {
+                float2 s[P];
+                if (P % 2 == 0) {
+#pragma unroll
+                    for (int p = 0; p < P; p += 2) {
+                        const float4 two = *reinterpret_cast<const float4 *>(rec + 16 + 8 * p);
+                        s[p] = make_float2(two.x, two.y);
+                        s[p + 1] = make_float2(two.z, two.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        s[p] = *reinterpret_cast<const float2 *>(rec + 16 + 8 * p);
+                }
+                const unsigned char *const urow = lut_bytes + (h.y & 0xffff) * (int) sizeof(float2);
+                const unsigned char *const vrow = lut_bytes + ((unsigned) h.y >> 16) * (int) sizeof(float2);
+                float2 wu[MX], wv[MY];
+#pragma unroll
+                for (int i = 0; i < MX; i++)
+                    wu[i] = *reinterpret_cast<const float2 *>(urow + xoff[i]);
+#pragma unroll
+                for (int j = 0; j < MY; j++)
+                    wv[j] = *reinterpret_cast<const float2 *>(vrow + yoff[j]);
+#pragma unroll
+                for (int j = 0; j < MY; j++)
+#pragma unroll
+                    for (int i = 0; i < MX; i++) {
+                        float2 wgt;
+                        wgt.x = wv[j].x * wu[i].x - wv[j].y * wu[i].y;
+                        wgt.y = wv[j].x * wu[i].y + wv[j].y * wu[i].x;
+#pragma unroll
+                        for (int p = 0; p < P; p++) {
+                            acc[j][i][p].x = fma((Real) s[p].x, (Real) wgt.x,
+                                                 fma((Real) s[p].y, (Real) wgt.y, acc[j][i][p].x));
+                            acc[j][i][p].y = fma((Real) s[p].y, (Real) wgt.x,
+                                                 fma(-(Real) s[p].x, (Real) wgt.y, acc[j][i][p].y));
+                        }
+                    }
+                rec += rec_stride;
+                if (++e >= GRID_TMA_BATCH) break;
+                h = *reinterpret_cast<const int4 *>(rec);
+                // leave the inner loop as a whole warp, so the lanes stay in lock step
+                if (__ballot_sync(lanes, (((unsigned) h.z & my_xmask)
+                                          | ((unsigned) h.w & my_ymask)) != 0) != 0)
+                    break;
+            }
+        }
+        // This warp is done with the stage.  Warps are not synchronised with each other:
+        // thread 0 refills the stage of the *previous* batch once every warp has left it,
+        // which leaves the copy two batches to land.
+        __syncwarp(lanes);
+        if ((tid & 31) == 0) mbar_arrive(empty + stage);
+        if (tid == 0 && b >= 1 && b - 1 + GRID_STAGES < my_batches) {
+            const int ps = (b - 1) % GRID_STAGES;
+            mbar_wait(empty + ps, ((b - 1) / GRID_STAGES) & 1);
+            mbar_expect_tx(full + ps, stage_bytes);
+            bulk_copy_g2s(ring + ps * stage_bytes, chunk_of(b - 1 + GRID_STAGES), stage_bytes,
+                          full + ps);
+        }
+    }
+    if (valid) flush_cells(~0u, ~0u);
+}
+
+// Library-managed scratch for the staged records (grows on demand, one per device).
+static unsigned char *g_scratch[64] = {nullptr};
+static size_t g_scratch_bytes[64] = {0};
+
+static int get_scratch(size_t bytes, unsigned char **out)
+{
+    int dev = 0;
+    KIB_CUDA(cudaGetDevice(&dev));
+    KIB_REQUIRE(dev >= 0 && dev < 64, "kib_grid: unsupported device index %d", dev);
+    if (g_scratch_bytes[dev] < bytes) {
+        if (g_scratch[dev] != nullptr) {
+            KIB_CUDA(cudaDeviceSynchronize());
+            KIB_CUDA(cudaFree(g_scratch[dev]));
+            g_scratch[dev] = nullptr;
+            g_scratch_bytes[dev] = 0;
+        }
+        const size_t want = bytes + bytes / 4;
+        KIB_CUDA(cudaMalloc(&g_scratch[dev], want));
+        g_scratch_bytes[dev] = want;
+    }
+    *out = g_scratch[dev];
+    return 0;
+}
+
 struct GridConfig {
     int mx, my, tx, ty;
 };
@@ -295,6 +757,15 @@ static bool choose_config(int K, int P, int dtype, GridConfig *out)
     return found;
 }
 
+template <typename Kernel>
+static int enable_large_smem(Kernel kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+        KIB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int) bytes));
+    return 0;
+}
+
 template <typename Real, int P, int MX, int MY>
 static int launch_grid(GridParams &prm, cudaStream_t stream)
 {
@@ -306,16 +777,94 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
     prm.groups_per_block = gpb;
     const int threads = gpb * group;
     // Enough groups to fill the machine a few times over, but runs long enough
-    // that the final flush (MX*MY*P reds per thread) stays negligible.
+    // that the final flush (MX*MY*P reds per thread) stays negligible.  Small launches
+    // (sparsely populated W slices) use short runs: their cost is latency, not work.
     const long long blocks_per_sm = 2048 / (threads < 64 ? 64 : threads);
     const long long target_groups = (long long) sm_count() * 2 * blocks_per_sm * gpb;
     long long run = (prm.num_vis + target_groups - 1) / target_groups;
-    if (run < 4 * GRID_BATCH) run = 4 * GRID_BATCH;
+    if (run < 4 * GRID_BATCH) {
+        // at least one full wave of blocks before runs get longer than one batch
+        const long long one_wave = (long long) sm_count() * gpb;
+        run = (prm.num_vis + one_wave - 1) / one_wave;
+        if (run > 4 * GRID_BATCH) run = 4 * GRID_BATCH;
+        if (run < GRID_BATCH) run = GRID_BATCH;
+    }
     if (run > 8192) run = 8192;
     run = (run + GRID_BATCH - 1) / GRID_BATCH * GRID_BATCH;
     prm.run = (int) run;
     const long long groups = (prm.num_vis + run - 1) / run;
     const long long blocks = (groups + gpb - 1) / gpb;
+
+    // Fast path when the doubled kernel table fits in shared memory (and slot masks in 32 bits)
+    const size_t rows = (size_t) prm.w_planes * prm.oversample;
+    const size_t lut_bytes = rows * 2 * (prm.bx + (prm.bx == prm.by ? 0 : prm.by)) * sizeof(float2);
+    if (lut_bytes <= (size_t) GRID_LUT_SMEM_LIMIT && lut_bytes / sizeof(float2) < 65536
+        && prm.bx <= 32 && prm.by <= 32 && prm.grid_size < 65536
+        && (long long) prm.grid_size * prm.grid_row_stride < (1ll << 32)) {
+        const int rec = grid_record_bytes(P);
+        const size_t stage_bytes = (size_t) GRID_TMA_BATCH * gpb * rec;
+        const size_t smem = 128 + GRID_STAGES * stage_bytes + lut_bytes;
+        const long long total = blocks * gpb * run;
+        unsigned char *scratch = nullptr;
+        const size_t table_bytes = (lut_bytes + 127) / 128 * 128;
+        int rc = get_scratch(table_bytes + (size_t) total * rec, &scratch);
+        if (rc != 0) return rc;
+        unsigned char *records = scratch + table_bytes;
+        float2 *tables = reinterpret_cast<float2 *>(scratch);
+        GridStageParams sp;
+        sp.records = records;
+        sp.weights_grid = prm.weights_grid;
+        sp.uv = prm.uv;
+        sp.w_plane = prm.w_plane;
+        sp.vis = prm.vis;
+        sp.num_rejected = prm.num_rejected;
+        sp.weights_pol_stride = prm.weights_pol_stride;
+        sp.num_vis = prm.num_vis;
+        sp.total = total;
+        sp.weights_row_stride = prm.weights_row_stride;
+        sp.grid_size = prm.grid_size;
+        sp.w_planes = prm.w_planes;
+        sp.oversample = prm.oversample;
+        sp.kernel_width = prm.kernel_width;
+        sp.uv_bias = prm.uv_bias;
+        sp.half_grid = prm.half_grid;
+        sp.bx = prm.bx;
+        sp.by = prm.by;
+        sp.groups_per_block = gpb;
+        sp.run = prm.run;
+        sp.lutv_base = prm.bx == prm.by ? 0 : (int) (rows * 2 * prm.bx);
+        sp.tables = tables;
+        sp.lut = prm.lut;
+        sp.lut_slice_stride = prm.lut_slice_stride;
+        sp.lut_tap_offset = prm.lut_tap_offset;
+        sp.lutx_count = (int) (rows * 2 * prm.bx);
+        sp.luty_count = prm.bx == prm.by ? 0 : (int) (rows * 2 * prm.by);
+        const long long stage_threads = total > sp.lutx_count + sp.luty_count
+            ? total : sp.lutx_count + sp.luty_count;
+        grid_stage_kernel<P><<<(unsigned) ((stage_threads + 255) / 256), 256, 0, stream>>>(sp);
+        prm.num_units = (int) blocks;
+        // One unit per block: the hardware block scheduler balances units of unequal cost
+        // (the kernel itself also supports fewer, persistent blocks).
+        const unsigned launch_blocks = (unsigned) blocks;
+#define KIB_LAUNCH_TMA(MAXT, MINB, TX1)                                                      \
+        do {                                                                                 \
+            auto kernel = grid_tma_kernel<Real, P, MX, MY, MAXT, MINB, TX1>;                  \
+            rc = enable_large_smem(kernel, smem);                                            \
+            if (rc != 0) return rc;                                                          \
+            kernel<<<launch_blocks, threads, smem, stream>>>(prm, records, tables);          \
+        } while (0)
+        if (threads <= 224) {
+            if (prm.tx == 1) KIB_LAUNCH_TMA(224, 3, true); else KIB_LAUNCH_TMA(224, 3, false);
+        } else if (threads <= 256) {
+            if (prm.tx == 1) KIB_LAUNCH_TMA(256, 2, true); else KIB_LAUNCH_TMA(256, 2, false);
+        } else {
+            KIB_LAUNCH_TMA(GRID_MAX_GROUP, 1, false);
+        }
+#undef KIB_LAUNCH_TMA
+        KIB_CHECK_LAUNCH();
+        return 0;
+    }
+
     const size_t smem = (size_t) gpb * GRID_BATCH * (sizeof(int4) + sizeof(int) + P * sizeof(float2));
     if (threads <= 256)
         grid_kernel<Real, P, MX, MY, 256><<<(unsigned) blocks, threads, smem, stream>>>(prm);
@@ -432,6 +981,8 @@ extern "C" int kib_grid(void *grid, int grid_row_stride, int64_t grid_pol_stride
     prm.ty = cfg.ty;
     prm.bx = cfg.mx * cfg.tx;
     prm.by = cfg.my * cfg.ty;
+    prm.magic_x = (unsigned) ((1ull << 32) / prm.bx) + 1;
+    prm.magic_y = (unsigned) ((1ull << 32) / prm.by) + 1;
     cudaStream_t s = as_stream(stream);
     if (dtype == KIB_F32) return dispatch_pols<float>(prm, cfg, num_pols, dtype, s);
     return dispatch_pols<double>(prm, cfg, num_pols, dtype, s);
