@@ -29,7 +29,7 @@ namespace kib {
 
 constexpr int GRID_BATCH = 16;          // visibilities staged per group per batch
 constexpr int GRID_MAX_GROUP = 512;      // largest thread group (one visibility stream)
-constexpr int GRID_MAX_GROUPS_PER_BLOCK = 32;
+constexpr int GRID_MAX_GROUPS_PER_BLOCK = 64;
 
 struct GridParams {
     void *grid;
@@ -284,7 +284,7 @@ grid_kernel(const GridParams prm)
 //    warp leaves it, the affected lanes flush, and the loop resumes.
 constexpr int GRID_LUT_SMEM_LIMIT = 96 * 1024;    // bytes of shared memory for the table
 constexpr int GRID_STAGES = 3;
-constexpr int GRID_TMA_BATCH = 8;                 // records per group per stage
+constexpr int GRID_TMA_BATCH = 16;                // records per group per stage
 
 __host__ __device__ constexpr int grid_record_bytes(int P) { return 16 + (8 * P + 15) / 16 * 16; }
 
@@ -853,9 +853,7 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
             if (rc != 0) return rc;                                                          \
             kernel<<<launch_blocks, threads, smem, stream>>>(prm, records, tables);          \
         } while (0)
-        if (threads <= 224) {
-            if (prm.tx == 1) KIB_LAUNCH_TMA(224, 3, true); else KIB_LAUNCH_TMA(224, 3, false);
-        } else if (threads <= 256) {
+        if (threads <= 256) {
             if (prm.tx == 1) KIB_LAUNCH_TMA(256, 2, true); else KIB_LAUNCH_TMA(256, 2, false);
         } else {
             KIB_LAUNCH_TMA(GRID_MAX_GROUP, 1, false);
