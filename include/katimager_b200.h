@@ -282,6 +282,19 @@ int kib_density_weights(float *grid, int row_stride, int64_t pol_stride, int wid
 int kib_fill(void *data, int row_stride, int64_t pol_stride, int width, int height,
              int num_pols, double value, int dtype, kib_stream_t stream);
 
+/* ------------------------------------------------------- visibility records
+ * Splits preprocessed visibility records (the array-of-structures layout of
+ * preprocess.cpp:39-52 minus w_slice: int16 uv[2], int16 sub_uv[2], int16 w_plane,
+ * 2 bytes padding, float weights[P], complex64 vis[P]; record_bytes = 12 + 12 P) that
+ * were uploaded in one block into the structure-of-arrays buffers the kernels use.
+ * Replaces the host-side field extraction of Imaging._set_uv / _set_buffer
+ * (imaging.py:269-314), which costs more than all device work of a step.
+ * Any output pointer may be NULL.  If vis_from_weights is non-zero, `vis` receives
+ * the weights as real numbers (the PSF pass grids the weights, frontend.py:511). */
+int kib_unpack_records(const void *records, int record_bytes, int64_t num_vis, int num_pols,
+                       int16_t *uv, int16_t *w_plane, float *weights, void *vis,
+                       int vis_from_weights, kib_stream_t stream);
+
 /* ------------------------------------------------------------------ predict
  * kib_predict replaces Predict._run (predict.py:386-416) + predict.mako:
  *   u = (uv.x*oversample + sub_u + 0.5)*uv_scale, v likewise, w = w_plane*w_scale + w_bias

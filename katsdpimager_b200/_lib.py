@@ -88,6 +88,7 @@ SIGNATURES = {
     'kib_mean_weight': [_vp, _i, _i, _i, _vp, _vp],
     'kib_density_weights': [_vp, _i, _i64, _i, _i, _i, _f, _f, _vp, _vp],
     'kib_fill': [_vp, _i, _i64, _i, _i, _i, _d, _i, _vp],
+    'kib_unpack_records': [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp],
     'kib_predict': [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _f, _vp],
     'kib_fp32_peak_kernel': [_vp, _i, _i, POINTER(c_double), _vp],
 }
@@ -137,7 +138,8 @@ _ONE_KERNEL = frozenset([
     'kib_image_to_layer', 'kib_scale', 'kib_add_image', 'kib_apply_primary_beam',
     'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
     'kib_abs_histogram', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
-    'kib_density_weights', 'kib_fill', 'kib_predict', 'kib_fp32_peak_kernel'])
+    'kib_density_weights', 'kib_fill', 'kib_predict', 'kib_fp32_peak_kernel',
+    'kib_unpack_records'])
 
 #: number of hand-written kernels launched through this module (cuFFT and memset/memcpy
 #: are not counted); bench.py reports the difference over its timed region

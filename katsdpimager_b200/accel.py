@@ -227,6 +227,18 @@ class HostArray(np.ndarray):
         return self._padded
 
 
+def is_pinned(array):
+    """True if `array` is (a view of) a :class:`HostArray`, i.e. lives in page-locked memory
+    that the copy engines can read without staging."""
+    while array is not None:
+        if isinstance(array, HostArray):
+            return True
+        if isinstance(array, ctypes.Array):
+            return hasattr(array, '_owner')
+        array = getattr(array, 'base', None)
+    return False
+
+
 class _PinnedOwner:
     def __init__(self, ptr):
         self._finalizer = weakref.finalize(self, _free_host, ptr)

@@ -477,7 +477,6 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
     constexpr int REC = grid_record_bytes(P);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int gpb = prm.groups_per_block;
-    const int K = prm.kernel_width;
     const int BX = prm.bx, BY = prm.by;
     const int G = prm.grid_size;
     const int rows = prm.w_planes * prm.oversample;
@@ -491,7 +490,6 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
     float2 *const lutx = reinterpret_cast<float2 *>(ring + GRID_STAGES * stage_bytes);
     const int lutx_count = rows * 2 * BX;
     const int luty_count = BX == BY ? 0 : rows * 2 * BY;
-    float2 *const luty = BX == BY ? lutx : lutx + lutx_count;
 
     const int tid = threadIdx.x;
     const unsigned lanes = __activemask();      // a block need not be a whole number of warps

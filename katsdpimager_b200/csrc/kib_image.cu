@@ -20,27 +20,44 @@ template <> struct Vec2<float> { typedef float2 type; };
 template <> struct Vec2<double> { typedef double2 type; };
 
 // ------------------------------------------------------------ grid -> layer (pad + ifftshift)
+// One thread writes two adjacent layer elements (one 16-byte store for complex64).  Layer
+// index f in [0, half) holds non-negative frequencies (grid index f + half); [N - half, N)
+// holds negative frequencies (grid index f - (N - half)); everything else is zero.
+template <typename Complex> struct Pair;
+template <> struct __align__(16) Pair<float2> { float2 a, b; };
+template <> struct __align__(32) Pair<double2> { double2 a, b; };
+
 template <typename Complex>
 __global__ void __launch_bounds__(256)
 grid_to_layer_kernel(Complex *__restrict__ layer, int layer_row_stride, int N,
                      const Complex *__restrict__ grid, int grid_row_stride, int G)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = blockIdx.y;
     if (x >= N) return;
     const int half = G / 2;
-    // Layer index f in [0, half) holds non-negative frequencies (grid index f + half);
-    // [N - half, N) holds negative frequencies (grid index f - (N - half)).
-    int gy = -1, gx = -1;
+    int gy = -1;
     if (y < half) gy = y + half;
     else if (y >= N - half) gy = y - (N - half);
-    if (x < half) gx = x + half;
-    else if (x >= N - half) gx = x - (N - half);
-    Complex value;
-    value.x = 0;
-    value.y = 0;
-    if (gy >= 0 && gx >= 0) value = grid[(long long) gy * grid_row_stride + gx];
-    layer[(long long) y * layer_row_stride + x] = value;
+    Pair<Complex> out;
+    out.a.x = out.a.y = out.b.x = out.b.y = 0;
+    if (gy >= 0) {
+        const Complex *row = grid + (long long) gy * grid_row_stride;
+        int gx0 = -1, gx1 = -1;
+        if (x < half) gx0 = x + half;
+        else if (x >= N - half) gx0 = x - (N - half);
+        if (x + 1 < half) gx1 = x + 1 + half;
+        else if (x + 1 >= N - half) gx1 = x + 1 - (N - half);
+        if (gx0 >= 0) out.a = __ldg(row + gx0);
+        if (gx1 >= 0) out.b = __ldg(row + gx1);
+    }
+    Complex *dst = layer + (long long) y * layer_row_stride + x;
+    if ((layer_row_stride & 1) == 0) {
+        *reinterpret_cast<Pair<Complex> *>(dst) = out;
+    } else {
+        dst[0] = out.a;
+        dst[1] = out.b;
+    }
 }
 
 template <typename Complex>
@@ -104,8 +121,9 @@ layer_image_kernel(Real *__restrict__ image, int image_row_stride,
     Real kx[2], ky[2], l2[2], m2[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        kx[i] = kernel1d[xs[i]];
-        ky[i] = kernel1d[ys[i]];
+        // reciprocal taper: the four pixels share two divisions per axis
+        kx[i] = (Real) 1 / kernel1d[xs[i]];
+        ky[i] = (Real) 1 / kernel1d[ys[i]];
         const Real l = add_rn(mul_rn((Real) xs[i], lm_scale), lm_bias);
         const Real m = add_rn(mul_rn((Real) ys[i], lm_scale), lm_bias);
         l2[i] = mul_rn(l, l);
@@ -124,10 +142,10 @@ layer_image_kernel(Real *__restrict__ image, int image_row_stride,
                 const Complex v = layer[laddr];
                 // Re(v * exp(2 pi i w (n - 1))) * n / (ky * kx)
                 const Real rotated = v.x * c - v.y * s;
-                image[iaddr] += rotated * n / (ky[i] * kx[j]);
+                image[iaddr] += rotated * n * (ky[i] * kx[j]);
             } else {
                 // image / (ky * kx * n) * exp(-2 pi i w (n - 1))
-                const Real v = image[iaddr] / (ky[i] * kx[j] * n);
+                const Real v = image[iaddr] * (ky[i] * kx[j]) / n;
                 Complex out;
                 out.x = v * c;
                 out.y = -(v * s);
@@ -217,7 +235,8 @@ int kib_grid_to_layer(void *layer, int layer_row_stride, int layer_size,
     KIB_REQUIRE(grid_size % 2 == 0 && grid_size <= layer_size && grid_size > 0,
                 "kib_grid_to_layer: grid size %d must be even and no larger than layer size %d",
                 grid_size, layer_size);
-    dim3 g = row_grid(layer_size, layer_size);
+    KIB_REQUIRE(layer_size % 2 == 0, "kib_grid_to_layer: odd layer size %d", layer_size);
+    dim3 g = row_grid(layer_size / 2, layer_size);
     if (dtype == KIB_F32)
         grid_to_layer_kernel<float2><<<g, 256, 0, as_stream(stream)>>>(
             static_cast<float2 *>(layer), layer_row_stride, layer_size,

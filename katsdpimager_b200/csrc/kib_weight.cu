@@ -93,6 +93,33 @@ density_weights_kernel(float *__restrict__ grid, int row_stride, long long pol_s
     block_accumulate<3>(v, sums);
 }
 
+// Array-of-structures visibility records -> structure-of-arrays device buffers
+__global__ void __launch_bounds__(256)
+unpack_records_kernel(const unsigned *__restrict__ records, int record_words, long long num_vis,
+                      int P, short4 *__restrict__ uv, short *__restrict__ w_plane,
+                      float *__restrict__ weights, float2 *__restrict__ vis, int vis_from_weights)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_vis) return;
+    const unsigned *rec = records + i * record_words;
+    if (uv != nullptr) {
+        const unsigned a = rec[0], b = rec[1];
+        uv[i] = make_short4((short) (a & 0xffff), (short) (a >> 16),
+                            (short) (b & 0xffff), (short) (b >> 16));
+    }
+    if (w_plane != nullptr) w_plane[i] = (short) (rec[2] & 0xffff);
+    for (int p = 0; p < P; p++) {
+        const float wt = __uint_as_float(rec[3 + p]);
+        if (weights != nullptr) weights[i * P + p] = wt;
+        if (vis != nullptr) {
+            vis[i * P + p] = vis_from_weights
+                ? make_float2(wt, 0.0f)
+                : make_float2(__uint_as_float(rec[3 + P + 2 * p]),
+                              __uint_as_float(rec[4 + P + 2 * p]));
+        }
+    }
+}
+
 static int reduction_blocks(long long total)
 {
     long long blocks = (total + 256 * 8 - 1) / (256 * 8);
@@ -118,6 +145,24 @@ int kib_grid_weights(float *grid, int row_stride, int64_t pol_stride, int width,
     grid_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
         grid, row_stride, pol_stride, width, height, reinterpret_cast<const short4 *>(uv),
         weights, num_pols, num_vis);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_unpack_records(const void *records, int record_bytes, int64_t num_vis, int num_pols,
+                       int16_t *uv, int16_t *w_plane, float *weights, void *vis,
+                       int vis_from_weights, kib_stream_t stream)
+{
+    KIB_REQUIRE(num_pols >= 1 && num_pols <= 4, "kib_unpack_records: num_pols must be 1..4");
+    KIB_REQUIRE(record_bytes == 12 + 12 * num_pols,
+                "kib_unpack_records: record size %d does not match %d polarizations",
+                record_bytes, num_pols);
+    if (num_vis <= 0) return 0;
+    const unsigned blocks = (unsigned) ((num_vis + 255) / 256);
+    unpack_records_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+        static_cast<const unsigned *>(records), record_bytes / 4, num_vis, num_pols,
+        reinterpret_cast<short4 *>(uv), w_plane, weights, static_cast<float2 *>(vis),
+        vis_from_weights);
     KIB_CHECK_LAUNCH();
     return 0;
 }

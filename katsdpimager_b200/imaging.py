@@ -14,7 +14,7 @@ scaling, primary-beam correction and the noise estimate.
 """
 import numpy as np
 
-from . import accel, clean, grid, image, predict, weight
+from . import _lib, accel, clean, grid, image, predict, weight
 from .profiling import profile_device, profile_function
 
 
@@ -77,6 +77,86 @@ def _uv_view(coords):
     quad = np.dtype(dict(names=['q'], formats=[('i2', (4,))], offsets=[uv_offset],
                          itemsize=coords.dtype.itemsize))
     return coords.view(quad)['q']
+
+
+class _RecordBlock:
+    """A block of preprocessed visibility records (array of structures, the layout of
+    reference preprocess.cpp:39-52) uploaded as is and split into the per-field device
+    buffers by ``kib_unpack_records``.
+
+    The reference extracts each field on the host into pinned staging
+    (``staging[:N] = chunk.field``, reference imaging.py:269-314); for strided record
+    fields that numpy copy costs more than all the device work of a chunk, so when the
+    caller hands over a contiguous record array the whole block makes one trip instead.
+    """
+
+    def __init__(self, command_queue, max_vis, num_polarizations):
+        self.command_queue = command_queue
+        self.num_polarizations = num_polarizations
+        self.record_bytes = 12 + 12 * num_polarizations
+        context = command_queue.context
+        self.device = accel.DeviceArray(context, (max_vis * self.record_bytes,), np.uint8)
+        self.staging = accel.HostArray((max_vis * self.record_bytes,), np.uint8, context=context)
+        self.staging_event = None
+        self.source = None          # (address, count) of the records now on the device
+
+    def matches(self, records):
+        """True if `records` is a contiguous record array with the expected layout."""
+        dtype = records.dtype
+        if dtype.names is None or records.ndim != 1 or dtype.itemsize != self.record_bytes \
+                or not records.flags.c_contiguous:
+            return False
+        P = self.num_polarizations
+        want = {'uv': (np.dtype(('i2', (2,))), 0), 'sub_uv': (np.dtype(('i2', (2,))), 4),
+                'w_plane': (np.dtype('i2'), 8), 'weights': (np.dtype(('f4', (P,))), 12),
+                'vis': (np.dtype(('c8', (P,))), 12 + 4 * P)}
+        return all(name in dtype.fields and dtype.fields[name][:2] == want[name] for name in want)
+
+    def field_of(self, array, name, count):
+        """True if `array` is field `name` of the record block currently on the device."""
+        if self.source is None or not isinstance(array, np.ndarray) or len(array) != count:
+            return False
+        address, n = self.source
+        P = self.num_polarizations
+        offset, dtype, inner = {'weights': (12, np.float32, (P,)),
+                                'vis': (12 + 4 * P, np.complex64, (P,)),
+                                'uv': (0, np.int16, (2,))}[name]
+        return (n == count and array.dtype == dtype and array.shape[1:] == inner
+                and array.ctypes.data == address + offset
+                and (count <= 1 or array.strides[0] == self.record_bytes)
+                and (array.ndim == 1 or array.strides[1] == array.dtype.itemsize))
+
+    def upload(self, records):
+        """Start the transfer of `records`.  Subsequent ``set_vis`` / ``set_weights`` calls
+        that pass fields of the same array (as frontend.make_dirty does) reuse this copy,
+        so the array must not be modified in between."""
+        count = len(records)
+        address = records.ctypes.data
+        nbytes = count * self.record_bytes
+        raw = records.view(np.uint8).reshape(-1)
+        queue = self.command_queue
+        if accel.is_pinned(records):
+            src = raw
+        else:
+            if self.staging_event is not None:
+                self.staging_event.wait()
+            self.staging[:nbytes] = raw         # one contiguous copy
+            src = self.staging
+        _lib.call('kib_memcpy_h2d_async', self.device.ptr, src.ctypes.data, nbytes, queue.stream)
+        if src is self.staging:
+            self.staging_event = queue.enqueue_marker()
+        self.source = (address, count)
+
+    def unpack(self, count, uv=None, w_plane=None, weights=None, vis=None, vis_from_weights=False):
+        def ptr(buffer):
+            return buffer.ptr if buffer is not None else None
+        with profile_device(self.command_queue, 'unpack_records'):
+            _lib.call('kib_unpack_records', self.device.ptr, self.record_bytes, count,
+                      self.num_polarizations, ptr(uv), ptr(w_plane), ptr(weights), ptr(vis),
+                      int(vis_from_weights), self.command_queue.stream)
+
+    def invalidate(self):
+        self.source = None
 
 
 #: compound slot -> member slots, as reference imaging.py:185-204
@@ -195,6 +275,7 @@ class Imaging(accel.OperationSequence):
             a.link(b)
         self.host_buffer = {name: _Staging(context, self.slots[name])
                             for name in ('weights', 'uv', 'w_plane', 'vis') if name in self.slots}
+        self._records = _RecordBlock(command_queue, max_vis, image_shape[0])
 
     def __call__(self, **kwargs):
         raise NotImplementedError()
@@ -226,17 +307,36 @@ class Imaging(accel.OperationSequence):
     def set_coordinates(self, coords):
         """Upload UVW coordinates from a record array with fields ``uv``, ``sub_uv``
         (adjacent int16 pairs) and ``w_plane``."""
+        if len(coords) != self.num_vis:
+            raise ValueError('Lengths do not match')
+        if self._records.matches(coords):
+            # whole records in one transfer, fields split on the device
+            self._records.upload(coords)
+            self._records.unpack(self.num_vis, uv=self.buffer('uv'), w_plane=self.buffer('w_plane'))
+            return
+        self._records.invalidate()
         self._set_buffer('uv', self.num_vis, _uv_view(coords))
         self._set_buffer('w_plane', self.num_vis, coords['w_plane'])
 
     @profile_function()
     def set_vis(self, vis):
-        self._set_buffer('vis', self.num_vis, vis)
+        N = self.num_vis
+        if self._records.field_of(vis, 'vis', N):
+            self._records.unpack(N, vis=self.buffer('vis'))
+        elif self._records.field_of(vis, 'weights', N):
+            # the PSF is made by gridding the weights (reference frontend.py:511)
+            self._records.unpack(N, vis=self.buffer('vis'), vis_from_weights=True)
+        else:
+            self._set_buffer('vis', N, vis)
 
     @profile_function()
     def set_weights(self, weights):
         """Set statistical weights for prediction"""
-        self._set_buffer('weights', self.num_vis, weights)
+        N = self.num_vis
+        if self._records.field_of(weights, 'weights', N):
+            self._records.unpack(N, weights=self.buffer('weights'))
+        else:
+            self._set_buffer('weights', N, weights)
 
     # ----------------------------------------------------------------------- weights
     @profile_function()

@@ -100,7 +100,7 @@ def test_grid_to_image_and_back(gpu, oracle, dtype):
     g2i()
     actual = g2i.buffer('image').get(queue)
     rms = np.sqrt(np.mean((actual - golden['image']) ** 2)) / np.abs(golden['image']).max()
-    assert rms < 5e-6
+    assert rms < (5e-6 if dtype == np.float32 else 2e-5)   # golden is single precision
     i2g = template.instantiate_image_to_grid(queue, (pols, size, size), fx['lm_scale'],
                                              fx['lm_bias'], plan)
     i2g.bind(layer=g2i.buffer('layer'), kernel1d=g2i.buffer('kernel1d'))
@@ -111,7 +111,7 @@ def test_grid_to_image_and_back(gpu, oracle, dtype):
     back = i2g.buffer('grid').get(queue)
     expected = cases.middle(golden['grid_from_model'], back.shape)
     rms = np.sqrt(np.mean(np.abs(back - expected) ** 2)) / np.abs(expected).max()
-    assert rms < 5e-6
+    assert rms < (5e-6 if dtype == np.float32 else 2e-5)   # golden is single precision
 
 
 def test_grid_to_image_w_precision(gpu, oracle):

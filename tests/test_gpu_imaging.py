@@ -77,3 +77,51 @@ def test_buffer_management(gpu):
     imager.num_vis = 3
     with pytest.raises(ValueError):
         imager.set_vis(np.zeros((4, 2), np.complex64))
+
+
+def test_record_upload_matches_field_upload(gpu):
+    """Uploading whole records and splitting them on the device (kib_unpack_records) gives
+    the same buffers as the reference's per-field host staging (imaging.py:269-314)."""
+    context, queue = gpu
+    fx = cases.imaging_case(num_baselines=30, num_dumps=20)
+    ip, gp, cp = fx['image_parameters'], fx['grid_parameters'], fx['clean_parameters']
+    wp = prm.WeightParameters(weight.WeightType.NATURAL)
+    template = imaging.ImagingTemplate(context, fx['array_parameters'], ip.fixed, wp, gp.fixed, cp)
+    imager = template.instantiate(queue, ip, gp, 1024, 0, 2)
+    imager.ensure_all_bound()
+    chunk = next(fx['reader'].iter_slice(0, 0, 500))
+    n = len(chunk)
+    assert n > 100
+    imager.num_vis = n
+
+    def snapshot():
+        return {name: imager.get_buffer(name)[:n].copy()
+                for name in ('uv', 'w_plane', 'vis', 'weights')}
+
+    # record path (contiguous record array)
+    assert imager._records.matches(chunk)
+    imager.set_coordinates(chunk)
+    imager.set_vis(chunk.vis)
+    imager.set_weights(chunk.weights)
+    via_records = snapshot()
+    np.testing.assert_array_equal(via_records['uv'][:, :2], chunk.uv)
+    np.testing.assert_array_equal(via_records['uv'][:, 2:], chunk.sub_uv)
+    np.testing.assert_array_equal(via_records['w_plane'], chunk.w_plane)
+    np.testing.assert_array_equal(via_records['vis'], chunk.vis)
+    np.testing.assert_array_equal(via_records['weights'], chunk.weights)
+    # PSF pass: the weights are gridded as if they were visibilities
+    imager.set_vis(chunk.weights)
+    np.testing.assert_array_equal(imager.get_buffer('vis')[:n], chunk.weights.astype(np.complex64))
+    # field path: detached copies are not recognised as fields of the uploaded block
+    for name in ('uv', 'w_plane', 'vis', 'weights'):
+        imager.buffer(name).zero(queue)
+    strided = chunk[::2]
+    assert not imager._records.matches(strided)
+    imager.num_vis = len(strided)
+    imager.set_coordinates(strided)
+    imager.set_vis(np.ascontiguousarray(strided.vis))
+    imager.set_weights(np.ascontiguousarray(strided.weights))
+    m = len(strided)
+    np.testing.assert_array_equal(imager.get_buffer('uv')[:m, :2], strided.uv)
+    np.testing.assert_array_equal(imager.get_buffer('vis')[:m], strided.vis)
+    np.testing.assert_array_equal(imager.get_buffer('weights')[:m], strided.weights)
