@@ -86,12 +86,41 @@ template <> __device__ __forceinline__ double add_rn(double a, double b) { retur
 template <typename Real>
 __device__ __forceinline__ void w_rotation(Real n, double w, Real *c, Real *s);
 
+// Single precision: the product w * (n - 1) is formed in float-float arithmetic (w split
+// on the host into hi + lo, product error recovered with an FMA) and reduced to
+// [-0.5, 0.5] turns with the 1.5 * 2^23 rounding constant; sin/cos come from degree-3
+// minimax polynomials in f^2 on the reduced quadrant (|f| <= 1/4 half-turn, abs error
+// < 1e-7).  Nothing here touches the XU (MUFU / conversion) pipe, which an earlier
+// version with double-precision reduction and sincospif() saturated (67 % busy).
+// Valid for |w (n - 1)| < 2^22 turns.
 template <>
 __device__ __forceinline__ void w_rotation<float>(float n, double w, float *c, float *s)
 {
-    const double phase = w * (double) __fadd_rn(n, -1.0f);
-    const float r = (float) (phase - rint(phase));
-    sincospif(2.0f * r, s, c);
+    const float MAGIC = 12582912.0f;                    // 1.5 * 2^23
+    const float w_hi = (float) w;                       // loop-invariant, hoisted by the compiler
+    const float w_lo = (float) (w - (double) w_hi);
+    const float nm1 = __fadd_rn(n, -1.0f);              // exact (n in [0.5, 1])
+    const float p = __fmul_rn(nm1, w_hi);
+    const float e = __fmaf_rn(nm1, w_hi, -p);           // exact rounding error of p
+    const float lo = __fmaf_rn(nm1, w_lo, e);
+    const float k = __fadd_rn(__fadd_rn(p, MAGIC), -MAGIC);     // rint(p)
+    const float t = 2.0f * __fadd_rn(__fadd_rn(p, -k), lo);     // phase in half-turns, |t| <= 1
+    // quadrant: t = j / 2 + f, |f| <= 1/4
+    const float jm = __fadd_rn(2.0f * t, MAGIC);
+    const int j = __float_as_int(jm);
+    const float f = __fmaf_rn(__fadd_rn(jm, -MAGIC), -0.5f, t);
+    const float z = f * f;
+    float sn = __fmaf_rn(z, -0.5893668532371521f, 2.5497970581054688f);
+    sn = __fmaf_rn(z, sn, -5.167708873748779f);
+    sn = __fmaf_rn(z, sn, 3.1415927410125732f) * f;
+    float cs = __fmaf_rn(z, -1.3069566488265991f, 4.0576629638671875f);
+    cs = __fmaf_rn(z, cs, -4.93479061126709f);
+    cs = __fmaf_rn(z, cs, 1.0f);
+    // rotate by j quarter turns: j & 1 swaps, signs from j & 2 and (j + 1) & 2
+    const float a = (j & 1) ? sn : cs;
+    const float b = (j & 1) ? cs : sn;
+    *c = __int_as_float(__float_as_int(a) ^ (((j + 1) & 2) << 30));
+    *s = __int_as_float(__float_as_int(b) ^ ((j & 2) << 30));
 }
 
 template <>
@@ -151,6 +180,67 @@ layer_image_kernel(Real *__restrict__ image, int image_row_stride,
                 out.y = -(v * s);
                 layer[laddr] = out;
             }
+        }
+}
+
+// Vectorised single-precision layer -> image: each thread handles two adjacent columns in
+// each of the four mirrored quadrants (8 pixels): 16-byte layer loads, 8-byte image
+// loads/stores.  Requires size / 2 even (all FFT-friendly sizes are multiples of 8).
+__global__ void __launch_bounds__(256)
+layer_to_image_x2_kernel(float *__restrict__ image, int image_row_stride,
+                         const float2 *__restrict__ layer, int layer_row_stride,
+                         int half, const float *__restrict__ kernel1d,
+                         float lm_scale, float lm_bias, double w)
+{
+    const int x0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int y0 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= half || y0 >= half) return;
+    const int xs[2] = {x0, x0 + half};
+    const int ys[2] = {y0, y0 + half};
+    // issue all loads first
+    float4 lay[2][2];
+    float2 img[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            lay[i][j] = *reinterpret_cast<const float4 *>(
+                layer + (long long) ys[1 - i] * layer_row_stride + xs[1 - j]);
+            img[i][j] = *reinterpret_cast<const float2 *>(
+                image + (long long) ys[i] * image_row_stride + xs[j]);
+        }
+    float kx[2][2], ky[2], l2[2][2], m2[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float2 k2 = *reinterpret_cast<const float2 *>(kernel1d + xs[i]);
+        kx[i][0] = 1.0f / k2.x;
+        kx[i][1] = 1.0f / k2.y;
+        ky[i] = 1.0f / kernel1d[ys[i]];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const float l = __fadd_rn(__fmul_rn((float) (xs[i] + q), lm_scale), lm_bias);
+            l2[i][q] = __fmul_rn(l, l);
+        }
+        const float m = __fadd_rn(__fmul_rn((float) ys[i], lm_scale), lm_bias);
+        m2[i] = __fmul_rn(m, m);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            float out[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const float n = sqrtf(__fadd_rn(1.0f, -__fadd_rn(m2[i], l2[j][q])));
+                float c, s;
+                w_rotation<float>(n, w, &c, &s);
+                const float vx = q == 0 ? lay[i][j].x : lay[i][j].z;
+                const float vy = q == 0 ? lay[i][j].y : lay[i][j].w;
+                const float rotated = vx * c - vy * s;
+                out[q] = (q == 0 ? img[i][j].x : img[i][j].y) + rotated * n * (ky[i] * kx[j][q]);
+            }
+            *reinterpret_cast<float2 *>(image + (long long) ys[i] * image_row_stride + xs[j]) =
+                make_float2(out[0], out[1]);
         }
 }
 
@@ -280,7 +370,17 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
     const int half = size / 2;
     dim3 block(32, 8, 1);
     dim3 g(divup(half, 32), divup(half, 8), 1);
-    if (dtype == KIB_F32)
+    if (dtype == KIB_F32 && half % 2 == 0 && image_row_stride % 2 == 0 && layer_row_stride % 2 == 0
+        && (reinterpret_cast<uintptr_t>(image_plane) & 7) == 0
+        && (reinterpret_cast<uintptr_t>(layer) & 15) == 0
+        && (reinterpret_cast<uintptr_t>(kernel1d) & 7) == 0) {
+        dim3 block2(64, 4, 1);
+        dim3 g2(divup(half / 2, 64), divup(half, 4), 1);
+        layer_to_image_x2_kernel<<<g2, block2, 0, as_stream(stream)>>>(
+            static_cast<float *>(image_plane), image_row_stride,
+            static_cast<const float2 *>(layer), layer_row_stride, half,
+            static_cast<const float *>(kernel1d), (float) lm_scale, (float) lm_bias, w);
+    } else if (dtype == KIB_F32)
         layer_image_kernel<float, true><<<g, block, 0, as_stream(stream)>>>(
             static_cast<float *>(image_plane), image_row_stride,
             static_cast<float2 *>(const_cast<void *>(layer)), layer_row_stride, half,
