@@ -99,6 +99,13 @@ int kib_fft_plan2d_create(kib_fft_plan_t *plan, int ny, int nx, int row_stride, 
 int kib_fft_plan2d_exec(kib_fft_plan_t plan, void *src, void *dst, int direction,
                         kib_stream_t stream);
 int kib_fft_plan2d_destroy(kib_fft_plan_t plan);
+/* Batched 1-D C2C plan: `batch` transforms of length n; consecutive elements of one
+ * transform are `stride` elements apart, consecutive transforms `dist` elements apart
+ * (same layout for input and output).  Executed/destroyed with kib_fft_plan2d_exec /
+ * kib_fft_plan2d_destroy.  Used to build the zero-row-skipping 2-D transform of the
+ * grid -> image stage (the grid occupies only G of the N layer rows). */
+int kib_fft_plan1d_create(kib_fft_plan_t *plan, int n, int64_t stride, int64_t dist,
+                          int batch, int dtype);
 
 /* ------------------------------------------------------------ grid / degrid
  * kib_grid replaces Gridder._run / static_run (grid.py:787-867) + grid.mako:63.
@@ -223,7 +230,9 @@ int kib_subtract_psf(void *dirty, void *model, int row_stride, int64_t pol_strid
  * to `components` (int32 y, int32 x, real value, real pixel[num_pols] laid out
  * as `component_stride` bytes per record) and increments state[0]; state[1] is
  * set to 1 when the threshold stopped the loop.  `state` is int32[4] device
- * memory zeroed by the caller before the first call of a batch. */
+ * memory zeroed by the caller before the first call of a batch.  `row_scratch` is
+ * tiles_y * (sizeof(real) + 4) bytes of device scratch (per-row tile maxima, rebuilt by
+ * every call, so the next peak is found without rescanning all tiles each cycle). */
 int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol_stride,
                            int width, int height, int num_pols, int border, int mode,
                            const void *psf, int psf_row_stride, int64_t psf_pol_stride,
@@ -234,7 +243,7 @@ int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol
                            void *peak_value, int32_t *peak_pos, void *peak_pixel,
                            double loop_gain, double threshold, int max_cycles,
                            void *components, int component_stride, int32_t *state,
-                           int dtype, kib_stream_t stream);
+                           void *row_scratch, int dtype, kib_stream_t stream);
 
 /* kib_psf_patch replaces PsfPatch.__call__ (clean.py:123-163) + psf_patch.mako:
  * bound[0] = max |x - mid_x|, bound[1] = max |y - mid_y| over pixels in

@@ -49,6 +49,7 @@ SIGNATURES = {
     'kib_memcpy_d2d_async': [_vp, _vp, _sz, _vp],
     'kib_memcpy3d_async': [_vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _sz, _i, _vp],
     'kib_fft_plan2d_create': [POINTER(c_void_p), _i, _i, _i, _i],
+    'kib_fft_plan1d_create': [POINTER(c_void_p), _i, _i64, _i64, _i, _i],
     'kib_fft_plan2d_exec': [_vp, _vp, _vp, _i, _vp],
     'kib_fft_plan2d_destroy': [_vp],
     'kib_grid': [_vp, _i, _i64, _i, _i,
@@ -80,7 +81,7 @@ SIGNATURES = {
                                _vp, _vp, _i, _i, _i,
                                _vp, _vp, _vp,
                                _d, _d, _i,
-                               _vp, _i, _vp, _i, _vp],
+                               _vp, _i, _vp, _vp, _i, _vp],
     'kib_psf_patch': [_vp, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _i, _vp],
     'kib_abs_histogram': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _vp, _i, _vp],
     'kib_rank': [_vp, _i, _i64, _i, _i, _i, _i, _d, _vp, _i, _vp],

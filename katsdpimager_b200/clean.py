@@ -491,6 +491,8 @@ class Clean(accel.OperationSequence):
         self._components = None
         self._components_host = None
         self._state = accel.DeviceArray(command_queue.context, (4,), np.int32)
+        self._row_scratch = accel.DeviceArray(
+            command_queue.context, (tile_shape[0] * (template.dtype.itemsize + 4),), np.uint8)
         self._state_host = accel.HostArray((4,), np.int32, context=command_queue.context)
         self._pending = []
         self._pending_key = None
@@ -555,7 +557,7 @@ class Clean(accel.OperationSequence):
                       self.buffer('peak_pixel').ptr,
                       float(params.loop_gain), float(threshold), int(max_cycles),
                       self._components.ptr, self._record_dtype.itemsize, self._state.ptr,
-                      _lib.dtype_code(dirty.dtype), queue.stream)
+                      self._row_scratch.ptr, _lib.dtype_code(dirty.dtype), queue.stream)
         self._state.get_async(queue, self._state_host)
         nbytes = max_cycles * self._record_dtype.itemsize
         _lib.call('kib_memcpy_d2h_async', self._components_host.ctypes.data,

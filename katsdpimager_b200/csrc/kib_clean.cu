@@ -178,6 +178,42 @@ find_peak_kernel(const Real *dirty, int row_stride, long long pol_stride, int P,
                    tiles_x, tiles_y, peak_value, peak_pos, peak_pixel, scratch);
 }
 
+// ------------------------------------------------------------------ per-row tile maxima
+// row_max[ty] = max over tx of tile_max[ty][tx], row_arg[ty] = first tx attaining it.
+// Lets the minor-cycle kernel find the global peak from (rows touched) x tiles_x + tiles_y
+// loads instead of scanning all tiles_y x tiles_x tiles every cycle.
+template <typename Real>
+__device__ __forceinline__ void tile_row_max(const Real *tile_max, int tile_stride, int tiles_x,
+                                             int ty, Real *row_max, int *row_arg)
+{
+    // one warp per row
+    const int lane = threadIdx.x & 31;
+    Best<Real> best;
+    best.value = -1;
+    best.key = INT_MAX;
+    for (int tx = lane; tx < tiles_x; tx += 32) {
+        const Real value = __ldcg(tile_max + (long long) ty * tile_stride + tx);
+        if (value > best.value) {
+            best.value = value;
+            best.key = tx;
+        }
+    }
+    best = warp_best(best);
+    if (lane == 0) {
+        row_max[ty] = best.value;
+        row_arg[ty] = best.key;
+    }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+tile_rows_kernel(const Real *tile_max, int tile_stride, int tiles_x, int tiles_y,
+                 Real *row_max, int *row_arg)
+{
+    const int ty = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ty < tiles_y) tile_row_max(tile_max, tile_stride, tiles_x, ty, row_max, row_arg);
+}
+
 // --------------------------------------------------------------------- subtract_psf
 template <typename Real>
 __global__ void __launch_bounds__(256)
@@ -219,6 +255,8 @@ struct CleanStepParams {
     int *peak_pos;
     void *peak_pixel;
     void *components;
+    void *row_max;        // per tile row: maximum of tile_max and the first column attaining it
+    int *row_arg;
     int *state;           // [0] cycles done, [1] stopped by threshold, [2] block ticket
     long long pol_stride;
     long long psf_pol_stride;
@@ -350,10 +388,44 @@ clean_step_kernel(const CleanStepParams prm)
     __syncthreads();
     if (is_last) {
         __threadfence();
-        find_peak_body(dirty, prm.row_stride, prm.pol_stride, P,
-                       static_cast<const Real *>(prm.tile_max), prm.tile_pos, prm.tile_stride,
-                       prm.tiles_x, prm.tiles_y, peak_value, prm.peak_pos, peak_pixel, scratch);
-        if (threadIdx.x == 0) state[2] = 0;
+        // Refresh the row maxima of the tile rows this cycle touched (one warp per row), then
+        // take the first maximum over rows: the same answer as np.argmax over all tiles.
+        Real *const row_max = static_cast<Real *>(prm.row_max);
+        const Real *const tile_max = static_cast<const Real *>(prm.tile_max);
+        int ty0 = floordiv32(cy0 - border), ty1 = floordiv32(cy1 - 1 - border) + 1;
+        if (ty0 < 0) ty0 = 0;
+        if (ty1 > prm.tiles_y) ty1 = prm.tiles_y;
+        for (int ty = ty0 + (threadIdx.x >> 5); ty < ty1; ty += CLEAN_THREADS / 32)
+            tile_row_max(tile_max, prm.tile_stride, prm.tiles_x, ty, row_max, prm.row_arg);
+        __syncthreads();
+        Best<Real> best;
+        best.value = -1;
+        best.key = INT_MAX;
+        for (int ty = threadIdx.x; ty < prm.tiles_y; ty += CLEAN_THREADS) {
+            const Real value = row_max[ty];
+            if (value > best.value) {
+                best.value = value;
+                best.key = ty;
+            }
+        }
+        best = block_best(best, scratch);
+        if (threadIdx.x == 0) {
+            int2 pos = make_int2(0, 0);
+            Real value = 0;
+            if (best.key != INT_MAX) {
+                const int ty = best.key, tx = prm.row_arg[ty];
+                pos = __ldcg(prm.tile_pos + (long long) ty * prm.tile_stride + tx);
+                value = best.value;
+            }
+            peak_value[0] = value;
+            prm.peak_pos[0] = pos.x;
+            prm.peak_pos[1] = pos.y;
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                peak_pixel[p] = __ldcg(dirty + p * prm.pol_stride
+                                       + (long long) pos.x * prm.row_stride + pos.y);
+            state[2] = 0;
+        }
     }
 }
 
@@ -564,9 +636,10 @@ int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol
                            void *peak_value, int32_t *peak_pos, void *peak_pixel,
                            double loop_gain, double threshold, int max_cycles,
                            void *components, int component_stride, int32_t *state,
-                           int dtype, kib_stream_t stream)
+                           void *row_scratch, int dtype, kib_stream_t stream)
 {
     KIB_CHECK_DTYPE("kib_clean_minor_cycles");
+    KIB_REQUIRE(row_scratch != nullptr, "kib_clean_minor_cycles: null row scratch");
     KIB_CHECK_MODE("kib_clean_minor_cycles");
     KIB_REQUIRE(patch_width >= 1 && patch_height >= 1 && patch_width <= psf_width
                 && patch_height <= psf_height, "kib_clean_minor_cycles: bad patch %d x %d",
@@ -586,6 +659,9 @@ int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol
     prm.peak_pos = peak_pos;
     prm.peak_pixel = peak_pixel;
     prm.components = components;
+    prm.row_max = row_scratch;
+    prm.row_arg = reinterpret_cast<int *>(static_cast<char *>(row_scratch)
+                                          + (size_t) tiles_y * (dtype == KIB_F32 ? 4 : 8));
     prm.state = state;
     prm.pol_stride = pol_stride;
     prm.psf_pol_stride = psf_pol_stride;
@@ -608,6 +684,18 @@ int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol
     // A patch of width w starting anywhere touches at most (w - 1) / 32 + 2 lattice cells.
     dim3 g((patch_width - 1) / TILE + 2, (patch_height - 1) / TILE + 2, 1);
     cudaStream_t s = as_stream(stream);
+    {
+        const int rows_per_block = 256 / 32;
+        const int blocks = divup(tiles_y, rows_per_block);
+        if (dtype == KIB_F32)
+            tile_rows_kernel<float><<<blocks, 256, 0, s>>>(
+                static_cast<const float *>(tile_max), tile_stride, tiles_x, tiles_y,
+                static_cast<float *>(prm.row_max), prm.row_arg);
+        else
+            tile_rows_kernel<double><<<blocks, 256, 0, s>>>(
+                static_cast<const double *>(tile_max), tile_stride, tiles_x, tiles_y,
+                static_cast<double *>(prm.row_max), prm.row_arg);
+    }
     for (int i = 0; i < max_cycles; i++) {
         int rc = dtype == KIB_F32 ? launch_step<float>(prm, num_pols, mode, g, s)
                                   : launch_step<double>(prm, num_pols, mode, g, s);

@@ -318,6 +318,35 @@ int kib_fft_plan2d_create(kib_fft_plan_t *plan, int ny, int nx, int row_stride, 
     return 0;
 }
 
+int kib_fft_plan1d_create(kib_fft_plan_t *plan, int n, int64_t stride, int64_t dist,
+                          int batch, int dtype)
+{
+    KIB_REQUIRE(plan != nullptr, "kib_fft_plan1d_create: null argument");
+    KIB_REQUIRE(n > 0 && batch > 0 && stride > 0 && dist > 0, "kib_fft_plan1d_create: bad shape");
+    KIB_REQUIRE(dtype == KIB_F32 || dtype == KIB_F64, "kib_fft_plan1d_create: bad dtype");
+    FftPlan *p = new FftPlan;
+    p->dtype = dtype;
+    cufftResult r = cufftCreate(&p->handle);
+    if (r != CUFFT_SUCCESS) {
+        delete p;
+        set_error("cufftCreate failed: %s", cufft_error_string(r));
+        return 1000 + (int) r;
+    }
+    long long len[1] = {n};
+    long long embed[1] = {n};
+    size_t work_size = 0;
+    r = cufftMakePlanMany64(p->handle, 1, len, embed, stride, dist, embed, stride, dist,
+                            dtype == KIB_F32 ? CUFFT_C2C : CUFFT_Z2Z, batch, &work_size);
+    if (r != CUFFT_SUCCESS) {
+        cufftDestroy(p->handle);
+        delete p;
+        set_error("cufftMakePlanMany64(1-D %d x %d) failed: %s", n, batch, cufft_error_string(r));
+        return 1000 + (int) r;
+    }
+    *plan = reinterpret_cast<kib_fft_plan_t>(p);
+    return 0;
+}
+
 int kib_fft_plan2d_exec(kib_fft_plan_t plan, void *src, void *dst, int direction,
                         kib_stream_t stream)
 {
