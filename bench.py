@@ -391,6 +391,10 @@ def run_gpu(args, ranks):
     clocks = sampler.stop()
     seconds = ranks.max(seconds)
     per_kernel = timer.device_seconds()
+    grid_calls = [stop_.time_since(start_) for start_, stop_ in timer.records.get('grid', [])]
+    slices_per_step = max(1, len(grid_calls) // args.steps)
+    grid_ms_per_slice = [1e3 * float(np.mean(grid_calls[i::slices_per_step]))
+                         for i in range(slices_per_step)]
     step_seconds = seconds / args.steps
     value = total_vis * ranks.world / step_seconds
 
@@ -446,6 +450,8 @@ def run_gpu(args, ranks):
             'bytes_per_launch': l2i_bytes},
         'kernels_ms_per_step': {k: v[1] / args.steps * 1e3 for k, v in sorted(per_kernel.items())},
         'channels_per_sec': ranks.world / step_seconds,
+        'grid_ms_per_slice': grid_ms_per_slice,
+        'vis_per_slice': [len(s) for s in slices if len(s)],
     }
     if ranks.rank == 0:
         if ranks.world == 1 and not args.no_cpu:

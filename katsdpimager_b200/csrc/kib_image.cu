@@ -244,6 +244,63 @@ layer_to_image_x2_kernel(float *__restrict__ image, int image_row_stride,
         }
 }
 
+// Vectorised single-precision image -> layer (mirror image of layer_to_image_x2_kernel).
+__global__ void __launch_bounds__(256)
+image_to_layer_x2_kernel(float2 *__restrict__ layer, int layer_row_stride,
+                         const float *__restrict__ image, int image_row_stride,
+                         int half, const float *__restrict__ kernel1d,
+                         float lm_scale, float lm_bias, double w)
+{
+    const int x0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int y0 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= half || y0 >= half) return;
+    const int xs[2] = {x0, x0 + half};
+    const int ys[2] = {y0, y0 + half};
+    float2 img[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+            img[i][j] = *reinterpret_cast<const float2 *>(
+                image + (long long) ys[i] * image_row_stride + xs[j]);
+    float kx[2][2], ky[2], l2[2][2], m2[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float2 k2 = *reinterpret_cast<const float2 *>(kernel1d + xs[i]);
+        kx[i][0] = 1.0f / k2.x;
+        kx[i][1] = 1.0f / k2.y;
+        ky[i] = 1.0f / kernel1d[ys[i]];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const float l = __fadd_rn(__fmul_rn((float) (xs[i] + q), lm_scale), lm_bias);
+            l2[i][q] = __fmul_rn(l, l);
+        }
+        const float m = __fadd_rn(__fmul_rn((float) ys[i], lm_scale), lm_bias);
+        m2[i] = __fmul_rn(m, m);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            float4 out;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const float n = sqrtf(__fadd_rn(1.0f, -__fadd_rn(m2[i], l2[j][q])));
+                float c, s;
+                w_rotation<float>(n, w, &c, &s);
+                const float v = (q == 0 ? img[i][j].x : img[i][j].y) * (ky[i] * kx[j][q]) / n;
+                if (q == 0) {
+                    out.x = v * c;
+                    out.y = -(v * s);
+                } else {
+                    out.z = v * c;
+                    out.w = -(v * s);
+                }
+            }
+            *reinterpret_cast<float4 *>(layer + (long long) ys[1 - i] * layer_row_stride + xs[1 - j]) = out;
+        }
+}
+
 // ------------------------------------------------------------ elementwise image ops
 struct ScaleFactors {
     double v[4];
@@ -404,7 +461,17 @@ int kib_image_to_layer(void *layer, int layer_row_stride,
     const int half = size / 2;
     dim3 block(32, 8, 1);
     dim3 g(divup(half, 32), divup(half, 8), 1);
-    if (dtype == KIB_F32)
+    if (dtype == KIB_F32 && half % 2 == 0 && image_row_stride % 2 == 0 && layer_row_stride % 2 == 0
+        && (reinterpret_cast<uintptr_t>(image_plane) & 7) == 0
+        && (reinterpret_cast<uintptr_t>(layer) & 15) == 0
+        && (reinterpret_cast<uintptr_t>(kernel1d) & 7) == 0) {
+        dim3 block2(64, 4, 1);
+        dim3 g2(divup(half / 2, 64), divup(half, 4), 1);
+        image_to_layer_x2_kernel<<<g2, block2, 0, as_stream(stream)>>>(
+            static_cast<float2 *>(layer), layer_row_stride,
+            static_cast<const float *>(image_plane), image_row_stride, half,
+            static_cast<const float *>(kernel1d), (float) lm_scale, (float) lm_bias, w);
+    } else if (dtype == KIB_F32)
         layer_image_kernel<float, false><<<g, block, 0, as_stream(stream)>>>(
             static_cast<float *>(const_cast<void *>(image_plane)), image_row_stride,
             static_cast<float2 *>(layer), layer_row_stride, half,
