@@ -94,7 +94,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(device), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -425,6 +425,10 @@ def run_gpu(args, ranks):
     else:
         hbm_peak, hbm_source = 6650.0, 'fallback (B200_PROFILING.md)'
 
+    traffic_file = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+    grid_traffic = (traffic['grid_dram_bytes_per_vis'] * vis_per_launch
+                    if 'grid_dram_bytes_per_vis' in traffic else None)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ranks.world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_seconds * 1e3,
@@ -435,19 +439,24 @@ def run_gpu(args, ranks):
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': e2e_seconds * 1e3},
         'roofline': {
-            'kernel': 'grid_kernel<float,4,7,1> (kib_grid.cu)', 'bound': 'fp32',
+            'kernel': 'grid_stage_kernel<4> + grid_tma_kernel<float,4,7,1> (kib_grid.cu)',
+            'bound': 'fp32',
             'achieved': achieved, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
-            'frac': achieved / (fp32_peak / 1e12), 'traffic': None,
+            'frac': achieved / (fp32_peak / 1e12), 'traffic': grid_traffic,
+            'traffic_note': 'DRAM bytes per launch from the committed ncu capture '
+                            '(profiles/r01_traffic.json), scaled to the average launch; '
+                            'algorithmic bytes are 58 B/vis, the staged records add 96 B/vis',
             'peak_source': 'FFMA micro-benchmark run in this process (burst); nominal 74.5',
             'flops_per_vis': flops_per_vis(KERNEL_WIDTH, POLS),
             'vis_per_launch': vis_per_launch, 'avg_launch_ms': grid_launch * 1e3},
         'roofline_epilogue': {
-            'kernel': 'layer_image_kernel<float,true> (kib_image.cu)', 'bound': 'hbm',
+            'kernel': 'layer_to_image_x2_kernel (kib_image.cu)', 'bound': 'hbm',
             'achieved': l2i_bytes / (l2i_seconds / max(l2i_count, 1)) / 1e9 if l2i_count else None,
             'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_source,
             'frac': (l2i_bytes / (l2i_seconds / max(l2i_count, 1)) / 1e9 / hbm_peak
                      if l2i_count else None),
-            'bytes_per_launch': l2i_bytes},
+            'bytes_per_launch': l2i_bytes,
+            'traffic': traffic.get('layer_to_image_dram_bytes_per_launch')},
         'kernels_ms_per_step': {k: v[1] / args.steps * 1e3 for k, v in sorted(per_kernel.items())},
         'channels_per_sec': ranks.world / step_seconds,
         'grid_ms_per_slice': grid_ms_per_slice,
@@ -467,7 +476,7 @@ def main():
     parser = argparse.ArgumentParser(description=__doc__,
                                      formatter_class=argparse.RawDescriptionHelpFormatter)
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=5)
+    parser.add_argument('--steps', type=int, default=20)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     parser.add_argument('--dumps', type=int, default=3600,
