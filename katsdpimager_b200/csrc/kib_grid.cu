@@ -600,10 +600,12 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
         for (int j = 0; j < MY; j++)
 #pragma unroll
             for (int i = 0; i < MX; i++)
+                if (hit[j][i]) {
 #pragma unroll
-                for (int p = 0; p < P; p++) {
-                    acc[j][i][p].x = hit[j][i] ? (Real) 0 : acc[j][i][p].x;
-                    acc[j][i][p].y = hit[j][i] ? (Real) 0 : acc[j][i][p].y;
+                    for (int p = 0; p < P; p++) {
+                        acc[j][i][p].x = 0;
+                        acc[j][i][p].y = 0;
+                    }
                 }
     };
 
@@ -789,6 +791,26 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
     }
     if (run > 8192) run = 8192;
     run = (run + GRID_BATCH - 1) / GRID_BATCH * GRID_BATCH;
+    if (threads <= 256) {
+        // A few waves of blocks: pick the run length (within -25 % .. +50 %) that leaves the
+        // last wave fullest, so no SM idles while a nearly empty wave drains.
+        const long long slots = (long long) sm_count() * 2;
+        double best_fill = -1.0;
+        long long best_run = run;
+        for (long long r = run - run / 4; r <= run + run / 2; r += GRID_BATCH) {
+            const long long rr = (r + GRID_BATCH - 1) / GRID_BATCH * GRID_BATCH;
+            if (rr < GRID_BATCH) continue;
+            const long long b = ((prm.num_vis + rr - 1) / rr + gpb - 1) / gpb;
+            const long long waves = (b + slots - 1) / slots;
+            const double fill = (double) b / (double) (waves * slots);
+            if (waves > 8) { best_run = run; break; }       // many waves: tail is negligible
+            if (fill > best_fill + 1e-9) {
+                best_fill = fill;
+                best_run = rr;
+            }
+        }
+        run = best_run;
+    }
     prm.run = (int) run;
     const long long groups = (prm.num_vis + run - 1) / run;
     const long long blocks = (groups + gpb - 1) / gpb;
