@@ -42,6 +42,7 @@ KERNEL_WIDTH = 7
 OVERSAMPLE = 8
 NUM_CHANNELS = 64
 VIS_BLOCK = 1 << 20
+E2E_DEPTH = 2            # imagers (command queues) in flight in the e2e leg
 METRIC = 'gridded_visibilities_per_sec'
 UNIT = 'vis/s'
 
@@ -333,22 +334,22 @@ def run_gpu(args, ranks):
             imager.grid()
             imager.grid_to_image(mid_w[w_slice])
 
-    def step_e2e(out):
-        imager.bind(**staging)
-        imager.clear_dirty()
+    def step_e2e(im, out):
+        """One channel through the Imaging facade from pinned HOST records to a pinned HOST
+        dirty image; everything is enqueued on the imager's own queue, nothing waits."""
+        im.clear_dirty()
         for w_slice, s in enumerate(pinned_slices):
             if len(s) == 0:
                 continue
-            imager.clear_grid()
+            im.clear_grid()
             for start in range(0, len(s), VIS_BLOCK):
                 chunk = s[start:start + VIS_BLOCK]
-                imager.num_vis = len(chunk)
-                imager.set_coordinates(chunk)
-                imager.set_vis(chunk.vis)
-                imager.grid()
-            imager.grid_to_image(mid_w[w_slice])
-        imager.buffer('dirty').get_async(queue, out)
-        queue.finish()
+                im.num_vis = len(chunk)
+                im.set_coordinates(chunk)
+                im.set_vis(chunk.vis)
+                im.grid()
+            im.grid_to_image(mid_w[w_slice])
+        im.buffer('dirty').get_async(im.command_queue, out)
 
     # ---- FP32 roofline denominator: FFMA micro-benchmark on all SMs
     sink = accel.DeviceArray(context, (1,), np.float32)
@@ -398,19 +399,35 @@ def run_gpu(args, ranks):
     step_seconds = seconds / args.steps
     value = total_vis * ranks.world / step_seconds
 
-    # ---- e2e: host buffers through the Imaging facade
-    dirty_host = imager.buffer('dirty').empty_like()
-    step_e2e(dirty_host)               # warm-up (page-locks, first touch)
+    # ---- e2e: host buffers through the Imaging facade.  Two imagers on two command queues
+    # take alternate channels (imaging.ImagingPipeline), so the record upload and image
+    # download of one step overlap the kernels of the next; every step still copies all of
+    # its inputs from pinned host memory and its dirty image back to the host.
+    queue.finish()
+    pipeline = imaging.ImagingPipeline(template, E2E_DEPTH, ip, gp, VIS_BLOCK, 0, 1)
+    dirty_host = []
+    for im in pipeline.imagers:
+        im.clear_weights()
+        im.finalize_weights()
+        dirty_host.append(im.buffer('dirty').empty_like())
+    for _ in range(len(pipeline)):      # warm-up (first touch, scratch allocation)
+        slot, im = pipeline.acquire()
+        step_e2e(im, dirty_host[slot])
+        pipeline.release(slot)
+    pipeline.finish()
     ranks.barrier()
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = queue.enqueue_marker()
+    e2e_steps = args.steps
+    t0 = pipeline.queues[0].enqueue_marker()
+    ends = []
     for _ in range(e2e_steps):
-        step_e2e(dirty_host)
-    t1 = queue.enqueue_marker()
-    t1.wait()
-    e2e_seconds = ranks.max(t1.time_since(t0)) / e2e_steps
+        slot, im = pipeline.acquire()
+        step_e2e(im, dirty_host[slot])
+        ends.append(pipeline.release(slot))
+    pipeline.finish()
+    e2e_seconds = ranks.max(max(e.time_since(t0) for e in ends[-len(pipeline):])) / e2e_steps
+    e2e_check = float(dirty_host[0][0, PIXELS // 2, PIXELS // 2])
     h2d = total_vis * slices[0].dtype.itemsize      # whole 60-byte records are uploaded
-    d2h = dirty_host.nbytes
+    d2h = dirty_host[0].nbytes
 
     # ---- roofline of the dominant hand-written kernel (gridder) and of the epilogue
     grid_count, grid_seconds = per_kernel.get('grid', (0, 0.0))
@@ -437,7 +454,8 @@ def run_gpu(args, ranks):
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': total_vis * ranks.world / e2e_seconds, 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': e2e_seconds * 1e3},
+                'ms_per_step': e2e_seconds * 1e3, 'steps': e2e_steps,
+                'queues_in_flight': E2E_DEPTH, 'centre_pixel': e2e_check},
         'roofline': {
             'kernel': 'grid_stage_kernel<4> + grid_tma_kernel<float,4,7,1> (kib_grid.cu)',
             'bound': 'fp32',

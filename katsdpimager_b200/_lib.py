@@ -67,6 +67,8 @@ SIGNATURES = {
     'kib_layer_to_grid': [_vp, _i, _i, _vp, _i, _i, _i, _vp],
     'kib_layer_to_image': [_vp, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
     'kib_image_to_layer': [_vp, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
+    'kib_grid_to_image': [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
+    'kib_grid_to_image_supported': [_i, _i, _i],
     'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
     'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
     'kib_apply_primary_beam': [_vp, _i, _i64, _vp, _i, _i, _i, _d, _d, _i, _vp],
@@ -153,8 +155,15 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
     if name in _ONE_KERNEL:
         kernel_launches += 1
+    elif name == 'kib_grid_to_image':
+        kernel_launches += 2                 # column pass + row pass
     elif name == 'kib_clean_minor_cycles':
         kernel_launches += int(args[26])     # one launch per requested cycle
+
+
+def grid_to_image_supported(size, grid_size, dtype):
+    """Whether the fused pruned transform (kib_grid_to_image) covers this case."""
+    return bool(load().kib_grid_to_image_supported(int(size), int(grid_size), dtype_code(dtype)))
 
 
 def dtype_code(dtype):

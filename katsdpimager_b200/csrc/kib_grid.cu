@@ -24,6 +24,9 @@
 //    loop reads them with two LDS.128 + P/2 LDS.128 and fetches its MX+MY
 //    convolution taps from the read-only LUT (L1 resident for small kernels).
 #include "kib_common.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace kib {
 
@@ -695,27 +698,33 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
     if (valid) flush_cells(~0u, ~0u);
 }
 
-// Library-managed scratch for the staged records (grows on demand, one per device).
-static unsigned char *g_scratch[64] = {nullptr};
-static size_t g_scratch_bytes[64] = {0};
+// Library-managed scratch for the staged records: grows on demand, one per (device,
+// stream) so that imagers running on different command queues do not share it.
+struct GridScratch {
+    unsigned char *data = nullptr;
+    size_t bytes = 0;
+};
+static std::mutex g_scratch_mutex;
+static std::map<std::pair<int, cudaStream_t>, GridScratch> g_scratch;
 
-static int get_scratch(size_t bytes, unsigned char **out)
+static int get_scratch(size_t bytes, cudaStream_t stream, unsigned char **out)
 {
     int dev = 0;
     KIB_CUDA(cudaGetDevice(&dev));
-    KIB_REQUIRE(dev >= 0 && dev < 64, "kib_grid: unsupported device index %d", dev);
-    if (g_scratch_bytes[dev] < bytes) {
-        if (g_scratch[dev] != nullptr) {
-            KIB_CUDA(cudaDeviceSynchronize());
-            KIB_CUDA(cudaFree(g_scratch[dev]));
-            g_scratch[dev] = nullptr;
-            g_scratch_bytes[dev] = 0;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    GridScratch &scratch = g_scratch[std::make_pair(dev, stream)];
+    if (scratch.bytes < bytes) {
+        if (scratch.data != nullptr) {
+            KIB_CUDA(cudaStreamSynchronize(stream));
+            KIB_CUDA(cudaFree(scratch.data));
+            scratch.data = nullptr;
+            scratch.bytes = 0;
         }
         const size_t want = bytes + bytes / 4;
-        KIB_CUDA(cudaMalloc(&g_scratch[dev], want));
-        g_scratch_bytes[dev] = want;
+        KIB_CUDA(cudaMalloc(&scratch.data, want));
+        scratch.bytes = want;
     }
-    *out = g_scratch[dev];
+    *out = scratch.data;
     return 0;
 }
 
@@ -827,7 +836,7 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
         const long long total = blocks * gpb * run;
         unsigned char *scratch = nullptr;
         const size_t table_bytes = (lut_bytes + 127) / 128 * 128;
-        int rc = get_scratch(table_bytes + (size_t) total * rec, &scratch);
+        int rc = get_scratch(table_bytes + (size_t) total * rec, stream, &scratch);
         if (rc != 0) return rc;
         unsigned char *records = scratch + table_bytes;
         float2 *tables = reinterpret_cast<float2 *>(scratch);

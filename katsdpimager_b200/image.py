@@ -280,15 +280,37 @@ class GridToImage(accel.OperationSequence):
         }
         super().__init__(command_queue, operations, compounds, allocator=allocator)
         self.slots['grid'] = accel.IOSlot(shape_grid, fft_plan.dtype_src)
+        #: use the fused pruned transform (kib_grid_to_image) when the library supports
+        #: the size; off until it beats the pad + cuFFT + layer_to_image sequence
+        self.fused = False
 
     def set_w(self, w):
         self._layer_to_image.set_w(w)
+
+    def _run_fused(self, grid, layer, polarizations, size, plane_bytes):
+        """Pruned transform with the layer_to_image arithmetic fused in
+        (csrc/kib_gridfft.cu); the layer buffer only holds the half-transformed columns."""
+        op = self._layer_to_image
+        image = self.buffer('image')
+        kernel1d = self.buffer('kernel1d')
+        image_plane = image.padded_shape[1] * image.padded_shape[2] * image.dtype.itemsize
+        for pol in range(polarizations):
+            with profile_device(self.command_queue, 'grid_to_image_fused'):
+                _lib.call('kib_grid_to_image',
+                          (image.ptr.value or 0) + pol * image_plane, image.padded_shape[2],
+                          (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
+                          layer.ptr, layer.padded_shape[1], layer.shape[1], kernel1d.ptr,
+                          float(op.lm_scale), float(op.lm_bias), float(op.w),
+                          _lib.dtype_code(grid.dtype), self.command_queue.stream)
 
     def _run(self):
         grid = self.buffer('grid')
         layer = self.buffer('layer')
         polarizations, size = _check_grid(grid, layer)
         plane_bytes = grid.padded_shape[1] * grid.padded_shape[2] * grid.dtype.itemsize
+        if self.fused and _lib.grid_to_image_supported(layer.shape[1], size, grid.dtype):
+            self._run_fused(grid, layer, polarizations, size, plane_bytes)
+            return
         for pol in range(polarizations):
             with profile_device(self.command_queue, 'grid_to_layer'):
                 _lib.call('kib_grid_to_layer', layer.ptr, layer.padded_shape[1], layer.shape[1],

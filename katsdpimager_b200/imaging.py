@@ -486,3 +486,60 @@ class Imaging(accel.OperationSequence):
         """Release the device memory of a buffer that is no longer needed."""
         if name in self.slots:
             self.slots[name].bind(None)
+
+
+class ImagingPipeline:
+    """Several :class:`Imaging` instances of one template, each on its own command queue,
+    handed out round-robin so that the host<->device copies of one channel overlap the
+    kernels of another (the reference's frontend images channels strictly one after the
+    other on one queue, reference frontend.py:583-692).
+
+    Typical use, one channel per turn::
+
+        slot, imager = pipeline.acquire()      # waits until that instance is idle
+        ... imager.set_coordinates / grid / grid_to_image ...
+        imager.buffer('dirty').get_async(imager.command_queue, host_image[slot])
+        pipeline.release(slot)                 # marks the end of this channel's work
+        ...
+        pipeline.wait(slot)                    # host_image[slot] is now valid
+
+    Everything an instance does stays ordered on its own queue; the only library state
+    shared between queues is read-only (kernel tables) or keyed by stream (the gridder's
+    staging scratch).
+    """
+
+    def __init__(self, template, depth, *args, **kwargs):
+        if depth < 1:
+            raise ValueError('depth must be at least 1')
+        self.queues = [template.context.create_command_queue() for _ in range(depth)]
+        self.imagers = [template.instantiate(queue, *args, **kwargs) for queue in self.queues]
+        for imager in self.imagers:
+            imager.ensure_all_bound()
+        self._done = [None] * depth
+        self._next = 0
+
+    def __len__(self):
+        return len(self.imagers)
+
+    def acquire(self):
+        """Next instance in turn, after its previously released work has completed."""
+        slot = self._next
+        self._next = (slot + 1) % len(self.imagers)
+        self.wait(slot)
+        return slot, self.imagers[slot]
+
+    def release(self, slot):
+        """Mark the end of the work enqueued on `slot` since :meth:`acquire`."""
+        self._done[slot] = self.queues[slot].enqueue_marker()
+        return self._done[slot]
+
+    def wait(self, slot):
+        if self._done[slot] is not None:
+            self._done[slot].wait()
+            self._done[slot] = None
+
+    def finish(self):
+        for slot in range(len(self.imagers)):
+            self.wait(slot)
+        for queue in self.queues:
+            queue.finish()
