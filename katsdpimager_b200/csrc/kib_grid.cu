@@ -61,6 +61,7 @@ struct GridParams {
     int group_size;          // TX*TY
     int groups_per_block;
     int run;                 // visibilities per group
+    int batch;               // fast path: records per group per ring stage (<= GRID_TMA_BATCH)
     unsigned magic_x, magic_y;   // floor(2^32 / BX) + 1: exact u % BX for u < 65536
     int num_units;               // work units (gpb groups x run visibilities each)
 };
@@ -311,6 +312,7 @@ struct GridStageParams {
     int bx, by;
     int groups_per_block;
     int run;
+    int batch;
     int lutv_base;               // offset of the v table in 8-byte units
     // doubled kernel tables (see grid_tma_kernel), built by the first threads
     float2 *tables;
@@ -359,11 +361,11 @@ grid_stage_kernel(const GridStageParams prm)
     // position of this visibility in the [block][batch][entry][group] layout
     const long long group_id = idx / prm.run;
     const int r = (int) (idx - group_id * prm.run);
-    const int batch = r / GRID_TMA_BATCH, e = r - batch * GRID_TMA_BATCH;
+    const int batch = r / prm.batch, e = r - batch * prm.batch;
     const long long block = group_id / prm.groups_per_block;
     const int g = (int) (group_id - block * prm.groups_per_block);
-    const int nbatches = prm.run / GRID_TMA_BATCH;
-    const long long slot = (((block * nbatches + batch) * GRID_TMA_BATCH + e)
+    const int nbatches = prm.run / prm.batch;
+    const long long slot = (((block * nbatches + batch) * prm.batch + e)
                             * prm.groups_per_block + g);
     unsigned char *rec = prm.records + slot * REC;
 
@@ -489,14 +491,15 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
     unsigned long long *const empty = full + GRID_STAGES;
     unsigned long long *const lut_bar = empty + GRID_STAGES;
     unsigned char *const ring = smem_raw + 128;
-    const int stage_bytes = GRID_TMA_BATCH * gpb * REC;
+    const int batch_len = prm.batch;
+    const int stage_bytes = batch_len * gpb * REC;
     float2 *const lutx = reinterpret_cast<float2 *>(ring + GRID_STAGES * stage_bytes);
     const int lutx_count = rows * 2 * BX;
     const int luty_count = BX == BY ? 0 : rows * 2 * BY;
 
     const int tid = threadIdx.x;
     const unsigned lanes = __activemask();      // a block need not be a whole number of warps
-    const int nbatches = prm.run / GRID_TMA_BATCH;
+    const int nbatches = prm.run / batch_len;
     // Persistent blocks: block k walks work units k, k + gridDim.x, ...; a unit is what
     // `gpb` groups grid in one run (gpb * run visibilities, `nbatches` ring stages).
     // Virtual batch vb of this block is batch vb % nbatches of its (vb / nbatches)-th unit.
@@ -626,7 +629,7 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
         // loop contains nothing but loads and FMAs on the register accumulators.
         int e = 0;
 #pragma unroll 1
-        while (e < GRID_TMA_BATCH) {
+        while (e < batch_len) {
             int4 h = *reinterpret_cast<const int4 *>(rec);
             if (((unsigned) h.z & my_xmask) | ((unsigned) h.w & my_ymask)) {
                 if (valid) flush_cells(h.z, h.w);
@@ -674,7 +677,7 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
                         }
                     }
                 rec += rec_stride;
-                if (++e >= GRID_TMA_BATCH) break;
+                if (++e >= batch_len) break;
                 h = *reinterpret_cast<const int4 *>(rec);
                 // leave the inner loop as a whole warp, so the lanes stay in lock step
                 if (__ballot_sync(lanes, (((unsigned) h.z & my_xmask)
@@ -820,6 +823,22 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
         }
         run = best_run;
     }
+    // Small launches (less than one wave of blocks) are bound by the length of the
+    // sequential chain of one group, not by throughput: give every group a shorter run,
+    // down to 4 visibilities, as long as the blocks still fit in one wave.
+    int batch = GRID_TMA_BATCH;
+    if (threads <= 256 && run == GRID_BATCH) {
+        const long long slots = (long long) sm_count() * 2;
+        for (int b = 4; b < GRID_TMA_BATCH; b *= 2) {
+            const long long blocks_b = ((prm.num_vis + b - 1) / b + gpb - 1) / gpb;
+            if (blocks_b <= slots) {
+                batch = b;
+                run = b;
+                break;
+            }
+        }
+    }
+    prm.batch = batch;
     prm.run = (int) run;
     const long long groups = (prm.num_vis + run - 1) / run;
     const long long blocks = (groups + gpb - 1) / gpb;
@@ -831,7 +850,7 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
         && prm.bx <= 32 && prm.by <= 32 && prm.grid_size < 65536
         && (long long) prm.grid_size * prm.grid_row_stride < (1ll << 32)) {
         const int rec = grid_record_bytes(P);
-        const size_t stage_bytes = (size_t) GRID_TMA_BATCH * gpb * rec;
+        const size_t stage_bytes = (size_t) prm.batch * gpb * rec;
         const size_t smem = 128 + GRID_STAGES * stage_bytes + lut_bytes;
         const long long total = blocks * gpb * run;
         unsigned char *scratch = nullptr;
@@ -861,6 +880,7 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
         sp.by = prm.by;
         sp.groups_per_block = gpb;
         sp.run = prm.run;
+        sp.batch = prm.batch;
         sp.lutv_base = prm.bx == prm.by ? 0 : (int) (rows * 2 * prm.bx);
         sp.tables = tables;
         sp.lut = prm.lut;
