@@ -25,6 +25,7 @@
 //    convolution taps from the read-only LUT (L1 resident for small kernels).
 #include "kib_common.cuh"
 #include <map>
+#include <type_traits>
 #include <mutex>
 #include <utility>
 
@@ -290,7 +291,13 @@ constexpr int GRID_LUT_SMEM_LIMIT = 96 * 1024;    // bytes of shared memory for 
 constexpr int GRID_STAGES = 3;
 constexpr int GRID_TMA_BATCH = 16;                // records per group per stage
 
-__host__ __device__ constexpr int grid_record_bytes(int P) { return 16 + (8 * P + 15) / 16 * 16; }
+// Record = header + weighted samples.  Narrow header (16 B): origin, two 16-bit table
+// offsets, two 32-bit slot masks.  Wide header (32 B, tables too large for shared memory
+// or more than 32 slots per axis): origin, two 32-bit table offsets, two 64-bit masks.
+__host__ __device__ constexpr int grid_record_bytes(int P, bool wide = false)
+{
+    return (wide ? 32 : 16) + (8 * P + 15) / 16 * 16;
+}
 
 struct GridStageParams {
     unsigned char *records;
@@ -321,28 +328,29 @@ struct GridStageParams {
     int lutx_count, luty_count;
 };
 
-__device__ __forceinline__ unsigned change_mask(int old_pos, int new_pos, int B)
+__device__ __forceinline__ unsigned long long change_mask(int old_pos, int new_pos, int B)
 {
     const int d = new_pos - old_pos;
-    if (d == 0) return 0u;
-    if (d >= B || -d >= B) return ~0u;
+    if (d == 0) return 0ull;
+    if (d >= B || -d >= B) return ~0ull;
     // d > 0: columns old .. old + d - 1 leave; d < 0: columns new .. new - d - 1 enter
     // (each takes over the slot of the column B cells away).
     int start = (d > 0 ? old_pos : new_pos) % B;
     const int count = d > 0 ? d : -d;
-    unsigned mask = 0;
+    unsigned long long mask = 0;
     for (int i = 0; i < count; i++) {
-        mask |= 1u << start;
+        mask |= 1ull << start;
         if (++start == B) start = 0;
     }
     return mask;
 }
 
-template <int P>
+template <int P, bool WIDE>
 __global__ void __launch_bounds__(256)
 grid_stage_kernel(const GridStageParams prm)
 {
-    constexpr int REC = grid_record_bytes(P);
+    constexpr int REC = grid_record_bytes(P, WIDE);
+    constexpr int HDR = WIDE ? 32 : 16;
     const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const int K = prm.kernel_width, G = prm.grid_size, BX = prm.bx, BY = prm.by;
     if (idx < prm.lutx_count + prm.luty_count) {
@@ -369,7 +377,9 @@ grid_stage_kernel(const GridStageParams prm)
                             * prm.groups_per_block + g);
     unsigned char *rec = prm.records + slot * REC;
 
-    int4 h = make_int4(0, BX | ((prm.lutv_base + BY) << 16), 0, 0);     // null record
+    // null record: origin 0, zero-weight taps (second half of a doubled row), no moves
+    int pos = 0, lutu = BX, lutv = prm.lutv_base + BY;
+    unsigned long long xm = 0, ym = 0;
     float2 v[P];
 #pragma unroll
     for (int p = 0; p < P; p++) v[p] = make_float2(0.0f, 0.0f);
@@ -387,13 +397,12 @@ grid_stage_kernel(const GridStageParams prm)
             u0 = 0; v0 = 0; w = 0; su = 0; sv = 0;
             if (prm.num_rejected != nullptr) atomicAdd(prm.num_rejected, 1);
         }
-        h.x = u0 | (v0 << 16);
-        const int lutu = ((w * prm.oversample + su) * 2 * BX) + BX - u0 % BX;
-        const int lutv = prm.lutv_base + ((w * prm.oversample + sv) * 2 * BY) + BY - v0 % BY;
-        h.y = lutu | (lutv << 16);
+        pos = u0 | (v0 << 16);
+        lutu = ((w * prm.oversample + su) * 2 * BX) + BX - u0 % BX;
+        lutv = prm.lutv_base + ((w * prm.oversample + sv) * 2 * BY) + BY - v0 % BY;
         if (r == 0) {
-            h.z = -1;       // first visibility of a run: every slot is new
-            h.w = -1;
+            xm = ~0ull;     // first visibility of a run: every slot is new
+            ym = ~0ull;
         } else {
             const short4 pc = prm.uv[idx - 1];
             const int pw = prm.w_plane[idx - 1];
@@ -403,8 +412,8 @@ grid_stage_kernel(const GridStageParams prm)
                              && pc.z >= 0 && pc.z < prm.oversample
                              && pc.w >= 0 && pc.w < prm.oversample;
             if (!pok) { pu = 0; pv = 0; }
-            h.z = (int) change_mask(pu, u0, BX);
-            h.w = (int) change_mask(pv, v0, BY);
+            xm = change_mask(pu, u0, BX);
+            ym = change_mask(pv, v0, BY);
         }
         if (ok) {
             const long long waddr = (long long) (c.y + prm.half_grid) * prm.weights_row_stride
@@ -418,8 +427,15 @@ grid_stage_kernel(const GridStageParams prm)
             }
         }
     }
-    *reinterpret_cast<int4 *>(rec) = h;
-    float2 *out = reinterpret_cast<float2 *>(rec + 16);
+    if (WIDE) {
+        reinterpret_cast<int4 *>(rec)[0] = make_int4(pos, lutu, lutv, 0);
+        reinterpret_cast<int4 *>(rec)[1] = make_int4((int) (unsigned) xm, (int) (unsigned) (xm >> 32),
+                                                     (int) (unsigned) ym, (int) (unsigned) (ym >> 32));
+    } else {
+        *reinterpret_cast<int4 *>(rec) = make_int4(pos, lutu | (lutv << 16),
+                                                   (int) (unsigned) xm, (int) (unsigned) ym);
+    }
+    float2 *out = reinterpret_cast<float2 *>(rec + HDR);
     if (P % 2 == 0) {
 #pragma unroll
         for (int p = 0; p < P; p += 2)
@@ -473,13 +489,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsign
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <typename Real, int P, int MX, int MY, int MAXT, int MINB, bool TX1>
+template <typename Real, int P, int MX, int MY, int MAXT, int MINB, bool TX1, bool WIDE>
 __global__ void __launch_bounds__(MAXT, MINB)
 grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
                 const float2 *__restrict__ tables)
 {
     typedef typename Acc<Real>::type Complex;
-    constexpr int REC = grid_record_bytes(P);
+    typedef typename std::conditional<WIDE, unsigned long long, unsigned>::type Mask;
+    constexpr int REC = grid_record_bytes(P, WIDE);
+    constexpr int HDR = WIDE ? 32 : 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int gpb = prm.groups_per_block;
     const int BX = prm.bx, BY = prm.by;
@@ -521,37 +539,41 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
         mbar_init(lut_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const unsigned table_bytes = (unsigned) ((lutx_count + luty_count) * sizeof(float2));
-        mbar_expect_tx(lut_bar, table_bytes);
-        bulk_copy_g2s(lutx, tables, table_bytes, lut_bar);
+        if (!WIDE) {
+            const unsigned table_bytes = (unsigned) ((lutx_count + luty_count) * sizeof(float2));
+            mbar_expect_tx(lut_bar, table_bytes);
+            bulk_copy_g2s(lutx, tables, table_bytes, lut_bar);
+        }
         for (int s = 0; s < GRID_STAGES && s < my_batches; s++) {
             mbar_expect_tx(full + s, stage_bytes);
             bulk_copy_g2s(ring + s * stage_bytes, chunk_of(s), stage_bytes, full + s);
         }
     }
     __syncthreads();        // barriers initialised
-    mbar_wait(lut_bar, 0);  // tables have landed
+    if (!WIDE) mbar_wait(lut_bar, 0);  // tables have landed
 
     const int g = tid / prm.group_size;
     const int q = tid - g * prm.group_size;
     const int ty = q / prm.tx;
     const int tx = q - ty * prm.tx;
-    const unsigned char *const lut_bytes = reinterpret_cast<const unsigned char *>(lutx);
+    // Tap tables: shared memory (narrow) or the global copy, read through L1 (wide)
+    const unsigned char *const lut_bytes = WIDE ? reinterpret_cast<const unsigned char *>(tables)
+                                                : reinterpret_cast<const unsigned char *>(lutx);
 
     // Per-thread slot constants
     int xoff[MX], yoff[MY];
-    unsigned my_xmask = 0, my_ymask = 0;
+    Mask my_xmask = 0, my_ymask = 0;
 #pragma unroll
     for (int i = 0; i < MX; i++) {
         const int s = TX1 ? i : tx + i * prm.tx;
         xoff[i] = s * (int) sizeof(float2);
-        my_xmask |= 1u << s;
+        my_xmask |= (Mask) 1 << s;
     }
 #pragma unroll
     for (int j = 0; j < MY; j++) {
         const int s = ty + j * prm.ty;
         yoff[j] = s * (int) sizeof(float2);
-        my_ymask |= 1u << s;
+        my_ymask |= (Mask) 1 << s;
     }
 
     Complex acc[MY][MX][P];
@@ -571,7 +593,7 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
     // Flush every accumulator selected by the masks to its cell under origin (pu0, pv0).
     // The reductions sit in branches but only read the accumulators; the zeroing is a
     // branch-free select so that the accumulators never change registers.
-    auto flush_cells = [&](unsigned xm, unsigned ym) {
+    auto flush_cells = [&](Mask xm, Mask ym) {
         const int pru = pu0 - BX * (int) __umulhi((unsigned) pu0, prm.magic_x);
         const int prv = pv0 - BY * (int) __umulhi((unsigned) pv0, prm.magic_y);
         bool hit[MY][MX];
@@ -620,7 +642,7 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
         const int stage = b % GRID_STAGES;
         if (b != 0 && b % nbatches == 0 && valid) {
             // next work unit: unrelated visibilities, start from clean accumulators
-            flush_cells(~0u, ~0u);
+            flush_cells(~(Mask) 0, ~(Mask) 0);
             valid = false;
         }
         mbar_wait(full + stage, (b / GRID_STAGES) & 1);
@@ -628,13 +650,32 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
         // ---- process the batch.  The flush lives in the outer loop so that the inner
         // loop contains nothing but loads and FMAs on the register accumulators.
         int e = 0;
+        // header of record `rec`: origin, table offsets (bytes) and this thread's move test
+        int pos, uoff, voff;
+        Mask xm, ym;
+        auto read_header = [&](const unsigned char *r) {
+            const int4 h = *reinterpret_cast<const int4 *>(r);
+            pos = h.x;
+            if (WIDE) {
+                const int4 m = *reinterpret_cast<const int4 *>(r + 16);
+                uoff = h.y * (int) sizeof(float2);
+                voff = h.z * (int) sizeof(float2);
+                xm = (Mask) (((unsigned long long) (unsigned) m.y << 32) | (unsigned) m.x);
+                ym = (Mask) (((unsigned long long) (unsigned) m.w << 32) | (unsigned) m.z);
+            } else {
+                uoff = (h.y & 0xffff) * (int) sizeof(float2);
+                voff = (int) ((unsigned) h.y >> 16) * (int) sizeof(float2);
+                xm = (Mask) (unsigned) h.z;
+                ym = (Mask) (unsigned) h.w;
+            }
+            return ((xm & my_xmask) | (ym & my_ymask)) != 0;
+        };
 #pragma unroll 1
         while (e < batch_len) {
-            int4 h = *reinterpret_cast<const int4 *>(rec);
-            if (((unsigned) h.z & my_xmask) | ((unsigned) h.w & my_ymask)) {
-                if (valid) flush_cells(h.z, h.w);
-                pu0 = h.x & 0xffff;
-                pv0 = (unsigned) h.x >> 16;
+            if (read_header(rec)) {
+                if (valid) flush_cells(xm, ym);
+                pu0 = pos & 0xffff;
+                pv0 = (unsigned) pos >> 16;
                 valid = true;
             }
 #pragma unroll 1
@@ -643,24 +684,26 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
                 if (P % 2 == 0) {
 #pragma unroll
                     for (int p = 0; p < P; p += 2) {
-                        const float4 two = *reinterpret_cast<const float4 *>(rec + 16 + 8 * p);
+                        const float4 two = *reinterpret_cast<const float4 *>(rec + HDR + 8 * p);
                         s[p] = make_float2(two.x, two.y);
                         s[p + 1] = make_float2(two.z, two.w);
                     }
                 } else {
 #pragma unroll
                     for (int p = 0; p < P; p++)
-                        s[p] = *reinterpret_cast<const float2 *>(rec + 16 + 8 * p);
+                        s[p] = *reinterpret_cast<const float2 *>(rec + HDR + 8 * p);
                 }
-                const unsigned char *const urow = lut_bytes + (h.y & 0xffff) * (int) sizeof(float2);
-                const unsigned char *const vrow = lut_bytes + ((unsigned) h.y >> 16) * (int) sizeof(float2);
+                const unsigned char *const urow = lut_bytes + uoff;
+                const unsigned char *const vrow = lut_bytes + voff;
                 float2 wu[MX], wv[MY];
 #pragma unroll
                 for (int i = 0; i < MX; i++)
-                    wu[i] = *reinterpret_cast<const float2 *>(urow + xoff[i]);
+                    wu[i] = WIDE ? __ldg(reinterpret_cast<const float2 *>(urow + xoff[i]))
+                                 : *reinterpret_cast<const float2 *>(urow + xoff[i]);
 #pragma unroll
                 for (int j = 0; j < MY; j++)
-                    wv[j] = *reinterpret_cast<const float2 *>(vrow + yoff[j]);
+                    wv[j] = WIDE ? __ldg(reinterpret_cast<const float2 *>(vrow + yoff[j]))
+                                 : *reinterpret_cast<const float2 *>(vrow + yoff[j]);
 #pragma unroll
                 for (int j = 0; j < MY; j++)
 #pragma unroll
@@ -678,10 +721,8 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
                     }
                 rec += rec_stride;
                 if (++e >= batch_len) break;
-                h = *reinterpret_cast<const int4 *>(rec);
                 // leave the inner loop as a whole warp, so the lanes stay in lock step
-                if (__ballot_sync(lanes, (((unsigned) h.z & my_xmask)
-                                          | ((unsigned) h.w & my_ymask)) != 0) != 0)
+                if (__ballot_sync(lanes, read_header(rec)) != 0)
                     break;
             }
         }
@@ -698,7 +739,7 @@ grid_tma_kernel(const GridParams prm, const unsigned char *__restrict__ records,
                           full + ps);
         }
     }
-    if (valid) flush_cells(~0u, ~0u);
+    if (valid) flush_cells(~(Mask) 0, ~(Mask) 0);
 }
 
 // Library-managed scratch for the staged records: grows on demand, one per (device,
@@ -843,15 +884,21 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
     const long long groups = (prm.num_vis + run - 1) / run;
     const long long blocks = (groups + gpb - 1) / gpb;
 
-    // Fast path when the doubled kernel table fits in shared memory (and slot masks in 32 bits)
+    // Fast path.  Narrow: the doubled kernel table fits in shared memory and a slot mask
+    // in 32 bits.  Wide: the table stays in global memory (read through L1) and masks are
+    // 64 bits, which covers every support up to 64 cells per axis.
     const size_t rows = (size_t) prm.w_planes * prm.oversample;
     const size_t lut_bytes = rows * 2 * (prm.bx + (prm.bx == prm.by ? 0 : prm.by)) * sizeof(float2);
-    if (lut_bytes <= (size_t) GRID_LUT_SMEM_LIMIT && lut_bytes / sizeof(float2) < 65536
-        && prm.bx <= 32 && prm.by <= 32 && prm.grid_size < 65536
-        && (long long) prm.grid_size * prm.grid_row_stride < (1ll << 32)) {
-        const int rec = grid_record_bytes(P);
+    const bool addressable = prm.grid_size < 65536
+        && (long long) prm.grid_size * prm.grid_row_stride < (1ll << 32);
+    const bool narrow = addressable && lut_bytes <= (size_t) GRID_LUT_SMEM_LIMIT
+        && lut_bytes / sizeof(float2) < 65536 && prm.bx <= 32 && prm.by <= 32;
+    const bool wide = addressable && !narrow && prm.bx <= 64 && prm.by <= 64
+        && lut_bytes / sizeof(float2) < (1u << 28);
+    if (narrow || wide) {
+        const int rec = grid_record_bytes(P, wide);
         const size_t stage_bytes = (size_t) prm.batch * gpb * rec;
-        const size_t smem = 128 + GRID_STAGES * stage_bytes + lut_bytes;
+        const size_t smem = 128 + GRID_STAGES * stage_bytes + (wide ? 0 : lut_bytes);
         const long long total = blocks * gpb * run;
         unsigned char *scratch = nullptr;
         const size_t table_bytes = (lut_bytes + 127) / 128 * 128;
@@ -890,22 +937,30 @@ static int launch_grid(GridParams &prm, cudaStream_t stream)
         sp.luty_count = prm.bx == prm.by ? 0 : (int) (rows * 2 * prm.by);
         const long long stage_threads = total > sp.lutx_count + sp.luty_count
             ? total : sp.lutx_count + sp.luty_count;
-        grid_stage_kernel<P><<<(unsigned) ((stage_threads + 255) / 256), 256, 0, stream>>>(sp);
+        const unsigned stage_blocks = (unsigned) ((stage_threads + 255) / 256);
+        if (wide)
+            grid_stage_kernel<P, true><<<stage_blocks, 256, 0, stream>>>(sp);
+        else
+            grid_stage_kernel<P, false><<<stage_blocks, 256, 0, stream>>>(sp);
         prm.num_units = (int) blocks;
         // One unit per block: the hardware block scheduler balances units of unequal cost
         // (the kernel itself also supports fewer, persistent blocks).
         const unsigned launch_blocks = (unsigned) blocks;
-#define KIB_LAUNCH_TMA(MAXT, MINB, TX1)                                                      \
+#define KIB_LAUNCH_TMA(MAXT, MINB, TX1, WIDE)                                                \
         do {                                                                                 \
-            auto kernel = grid_tma_kernel<Real, P, MX, MY, MAXT, MINB, TX1>;                  \
+            auto kernel = grid_tma_kernel<Real, P, MX, MY, MAXT, MINB, TX1, WIDE>;            \
             rc = enable_large_smem(kernel, smem);                                            \
             if (rc != 0) return rc;                                                          \
             kernel<<<launch_blocks, threads, smem, stream>>>(prm, records, tables);          \
         } while (0)
-        if (threads <= 256) {
-            if (prm.tx == 1) KIB_LAUNCH_TMA(256, 2, true); else KIB_LAUNCH_TMA(256, 2, false);
+        if (wide) {
+            if (threads <= 256) KIB_LAUNCH_TMA(256, 2, false, true);
+            else KIB_LAUNCH_TMA(GRID_MAX_GROUP, 1, false, true);
+        } else if (threads <= 256) {
+            if (prm.tx == 1) KIB_LAUNCH_TMA(256, 2, true, false);
+            else KIB_LAUNCH_TMA(256, 2, false, false);
         } else {
-            KIB_LAUNCH_TMA(GRID_MAX_GROUP, 1, false);
+            KIB_LAUNCH_TMA(GRID_MAX_GROUP, 1, false, false);
         }
 #undef KIB_LAUNCH_TMA
         KIB_CHECK_LAUNCH();
