@@ -42,7 +42,7 @@ KERNEL_WIDTH = 7
 OVERSAMPLE = 8
 NUM_CHANNELS = 64
 VIS_BLOCK = 1 << 20
-E2E_DEPTH = 2            # imagers (command queues) in flight in the e2e leg
+E2E_DEPTH = int(os.environ.get('KIB_E2E_DEPTH', '3'))   # imagers (command queues) in flight in the e2e leg
 METRIC = 'gridded_visibilities_per_sec'
 UNIT = 'vis/s'
 
@@ -399,8 +399,8 @@ def run_gpu(args, ranks):
     step_seconds = seconds / args.steps
     value = total_vis * ranks.world / step_seconds
 
-    # ---- e2e: host buffers through the Imaging facade.  Two imagers on two command queues
-    # take alternate channels (imaging.ImagingPipeline), so the record upload and image
+    # ---- e2e: host buffers through the Imaging facade.  E2E_DEPTH imagers on their own command
+    # queues take channels in turn (imaging.ImagingPipeline), so the record upload and image
     # download of one step overlap the kernels of the next; every step still copies all of
     # its inputs from pinned host memory and its dirty image back to the host.
     queue.finish()

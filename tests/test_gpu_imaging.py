@@ -125,3 +125,71 @@ def test_record_upload_matches_field_upload(gpu):
     np.testing.assert_array_equal(imager.get_buffer('uv')[:m, :2], strided.uv)
     np.testing.assert_array_equal(imager.get_buffer('vis')[:m], strided.vis)
     np.testing.assert_array_equal(imager.get_buffer('weights')[:m], strided.weights)
+
+
+def test_imaging_pipeline_matches_single_imager(gpu):
+    """Two imagers on two command queues taking alternate channels (ImagingPipeline, as
+    bench.py's e2e leg does) produce the dirty image a single imager produces; all work of
+    a turn stays asynchronous until wait()."""
+    context, queue = gpu
+    fx = cases.imaging_case(num_baselines=30, num_dumps=20)
+    ip, gp, cp = fx['image_parameters'], fx['grid_parameters'], fx['clean_parameters']
+    wp = prm.WeightParameters(weight.WeightType.NATURAL)
+    template = imaging.ImagingTemplate(context, fx['array_parameters'], ip.fixed, wp, gp.fixed, cp)
+    mid_w = prm.slice_mid_w(ip, gp)
+    reader = fx['reader']
+
+    def dirty_image(imager, scale):
+        imager.clear_dirty()
+        for w_slice in range(reader.num_w_slices(0)):
+            if reader.len(0, w_slice) == 0:
+                continue
+            imager.clear_grid()
+            for chunk in reader.iter_slice(0, w_slice, 1024):
+                imager.num_vis = len(chunk)
+                imager.set_coordinates(chunk)
+                imager.set_vis(chunk.vis * np.complex64(scale))
+                imager.grid()
+            imager.grid_to_image(mid_w[w_slice])
+
+    single = template.instantiate(queue, ip, gp, 1024, 0, 2)
+    single.ensure_all_bound()
+    single.clear_weights()
+    single.finalize_weights()
+    expected = {}
+    for scale in (1.0, 2.0, 3.0):
+        dirty_image(single, scale)
+        expected[scale] = single.get_buffer('dirty').copy()
+    assert np.abs(expected[1.0]).max() > 0
+
+    pipeline = imaging.ImagingPipeline(template, 2, ip, gp, 1024, 0, 2)
+    assert len(pipeline) == 2
+    hosts = []
+    for imager in pipeline.imagers:
+        imager.clear_weights()
+        imager.finalize_weights()
+        hosts.append(imager.buffer('dirty').empty_like())
+    got = {}
+    pending = {}
+    for scale in (1.0, 2.0, 3.0):
+        slot, imager = pipeline.acquire()
+        if slot in pending:                      # acquire() waited: the host copy is valid
+            got[pending.pop(slot)] = hosts[slot].copy()
+        dirty_image(imager, scale)
+        imager.buffer('dirty').get_async(imager.command_queue, hosts[slot])
+        pipeline.release(slot)
+        pending[slot] = scale
+    pipeline.finish()
+    for slot, scale in pending.items():
+        got[scale] = hosts[slot].copy()
+    # The order of the gridder's reductions differs from run to run (3e-8 of the largest grid
+    # cell); dividing by the taper amplifies that towards the image edges, so two runs of the
+    # SAME imager differ by ~1e-4 of the peak at worst and ~1e-5 RMS (profiles/pipe_diag.py).
+    for scale in (1.0, 2.0, 3.0):
+        assert _rms_rel(got[scale], expected[scale]) < 1e-4
+        assert np.abs(got[scale] - expected[scale]).max() < 5e-3 * np.abs(expected[scale]).max()
+    assert _rms_rel(got[2.0], 2 * expected[1.0]) < 1e-4      # each turn saw its own data
+    assert _rms_rel(got[3.0], 3 * expected[1.0]) < 1e-3
+    assert _rms_rel(got[3.0], expected[1.0]) > 0.5
+    with pytest.raises(ValueError):
+        imaging.ImagingPipeline(template, 0, ip, gp, 1024, 0, 2)
