@@ -269,7 +269,7 @@ def workload_config(total_vis, args, world):
     return {
         'workload': ('BASELINE configs[1]: MeerKAT-64 L-band 4-pol, 8192^2 image, 16 w-slices, '
                      '7x7 support x8 oversample; one channel per GPU per step (dirty image: '
-                     'grid all slices + pad/ifftshift + cuFFT + layer_to_image)'),
+                     'grid all slices + fused pruned grid->image transform per plane)'),
         'pixels': PIXELS, 'polarizations': POLS, 'w_slices': W_SLICES, 'w_planes': W_PLANES,
         'kernel_width': KERNEL_WIDTH, 'oversample': OVERSAMPLE,
         'vis_per_channel': int(total_vis), 'dumps': args.dumps, 'channels_per_step': world,
@@ -429,23 +429,61 @@ def run_gpu(args, ranks):
     h2d = total_vis * slices[0].dtype.itemsize      # whole 60-byte records are uploaded
     d2h = dirty_host[0].nbytes
 
-    # ---- roofline of the dominant hand-written kernel (gridder) and of the epilogue
+    # ---- rooflines.  `roofline` is the kernel that takes most of the step, the row pass of the
+    # fused grid -> image transform (HBM roofline over its ALGORITHMIC bytes: the half-transformed
+    # plane read once, the image plane read and written once); the column pass and the gridder
+    # (FP32 pipe, the north star's named kernel) follow as extra objects.
     grid_count, grid_seconds = per_kernel.get('grid', (0, 0.0))
     grid_launch = grid_seconds / max(grid_count, 1)
     vis_per_launch = total_vis * args.steps / max(grid_count, 1)
     achieved = vis_per_launch * flops_per_vis(KERNEL_WIDTH, POLS) / grid_launch / 1e12
-    l2i_count, l2i_seconds = per_kernel.get('layer_to_image', (0, 0.0))
-    l2i_bytes = 16.0 * PIXELS * PIXELS
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_file):
         hbm_peak, hbm_source = json.load(open(peaks_file))['hbm_gbs'], 'MEASURED_PEAKS.json'
     else:
         hbm_peak, hbm_source = 6650.0, 'fallback (B200_PROFILING.md)'
-
     traffic_file = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
     grid_traffic = (traffic['grid_dram_bytes_per_vis'] * vis_per_launch
                     if 'grid_dram_bytes_per_vis' in traffic else None)
+    grid_size = imager.buffer('grid').shape[-1]
+
+    def hbm_roofline(name, kernel, nbytes, traffic_key, note):
+        count, seconds = per_kernel.get(name, (0, 0.0))
+        if not count:
+            return None
+        gbs = nbytes / (seconds / count) / 1e9
+        return {'kernel': kernel, 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak,
+                'unit': 'GB/s', 'frac': gbs / hbm_peak, 'traffic': traffic.get(traffic_key),
+                'peak_source': hbm_source, 'bytes_per_launch': nbytes,
+                'avg_launch_ms': seconds / count * 1e3, 'launches_per_step': count / args.steps,
+                'note': note}
+
+    rows_roofline = hbm_roofline(
+        'grid_to_image_rows', 'rows_kernel<8192,256,16,16,2> (kib_gridfft.cu)',
+        8.0 * PIXELS * grid_size + 8.0 * PIXELS * PIXELS, 'fused_rows_dram_bytes_per_launch',
+        'algorithmic bytes = 8 N G (half-transformed plane) + 8 N^2 (image read + write); the '
+        'kernel is issue-bound (77 % of issue slots busy, profiles/r01_fused_fft_ncu_summary.csv)')
+    columns_roofline = hbm_roofline(
+        'grid_to_image_columns', 'columns_kernel (kib_gridfft.cu)',
+        8.0 * grid_size * grid_size + 8.0 * PIXELS * grid_size,
+        'fused_columns_dram_bytes_per_launch',
+        'algorithmic bytes = 8 G^2 (grid plane) + 8 N G (half-transformed plane written)')
+    epilogue_roofline = hbm_roofline(
+        'layer_to_image', 'layer_to_image_x2_kernel (kib_image.cu; cuFFT route only)',
+        16.0 * PIXELS * PIXELS, 'layer_to_image_dram_bytes_per_launch',
+        '16 B per pixel: layer read, image read + write')
+    gridder_roofline = {
+        'kernel': 'grid_stage_kernel<4> + grid_tma_kernel<float,4,7,1> (kib_grid.cu)',
+        'bound': 'fp32',
+        'achieved': achieved, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
+        'frac': achieved / (fp32_peak / 1e12), 'traffic': grid_traffic,
+        'traffic_note': 'DRAM bytes per launch from the committed ncu capture '
+                        '(profiles/r01_traffic.json), scaled to the average launch; '
+                        'algorithmic bytes are 58 B/vis, the staged records add 96 B/vis',
+        'peak_source': 'FFMA micro-benchmark run in this process (burst); nominal 74.5',
+        'flops_per_vis': flops_per_vis(KERNEL_WIDTH, POLS),
+        'vis_per_launch': vis_per_launch, 'avg_launch_ms': grid_launch * 1e3}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ranks.world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_seconds * 1e3,
@@ -456,25 +494,9 @@ def run_gpu(args, ranks):
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': e2e_seconds * 1e3, 'steps': e2e_steps,
                 'queues_in_flight': E2E_DEPTH, 'centre_pixel': e2e_check},
-        'roofline': {
-            'kernel': 'grid_stage_kernel<4> + grid_tma_kernel<float,4,7,1> (kib_grid.cu)',
-            'bound': 'fp32',
-            'achieved': achieved, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
-            'frac': achieved / (fp32_peak / 1e12), 'traffic': grid_traffic,
-            'traffic_note': 'DRAM bytes per launch from the committed ncu capture '
-                            '(profiles/r01_traffic.json), scaled to the average launch; '
-                            'algorithmic bytes are 58 B/vis, the staged records add 96 B/vis',
-            'peak_source': 'FFMA micro-benchmark run in this process (burst); nominal 74.5',
-            'flops_per_vis': flops_per_vis(KERNEL_WIDTH, POLS),
-            'vis_per_launch': vis_per_launch, 'avg_launch_ms': grid_launch * 1e3},
-        'roofline_epilogue': {
-            'kernel': 'layer_to_image_x2_kernel (kib_image.cu)', 'bound': 'hbm',
-            'achieved': l2i_bytes / (l2i_seconds / max(l2i_count, 1)) / 1e9 if l2i_count else None,
-            'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_source,
-            'frac': (l2i_bytes / (l2i_seconds / max(l2i_count, 1)) / 1e9 / hbm_peak
-                     if l2i_count else None),
-            'bytes_per_launch': l2i_bytes,
-            'traffic': traffic.get('layer_to_image_dram_bytes_per_launch')},
+        'roofline': rows_roofline if rows_roofline is not None else epilogue_roofline,
+        'roofline_columns': columns_roofline,
+        'roofline_gridder': gridder_roofline,
         'kernels_ms_per_step': {k: v[1] / args.steps * 1e3 for k, v in sorted(per_kernel.items())},
         'channels_per_sec': ranks.world / step_seconds,
         'grid_ms_per_slice': grid_ms_per_slice,

@@ -165,15 +165,25 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
 /* kib_grid_to_image replaces the whole per-polarization body of GridToImage._run
  * (image.py:655-673: layer memset + 4 quadrant copies, the inverse cuFFT of
  * image.py:649-653, and LayerToImage) by a pruned, fused transform that never builds
- * the zero-padded layer: an inverse DFT along the rows of the grid_size^2 grid
- * (only the non-zero columns), then one size-point inverse FFT per image row in
- * shared memory with the layer_to_image arithmetic applied from registers.
- * `scratch` holds size rows of at least grid_size complex values (the reference's
- * layer buffer is large enough).  Single precision and size in {1024, 2048, 4096,
- * 8192, 16384} only; kib_grid_to_image_supported returns 1 for supported
- * combinations and 0 otherwise (callers then use kib_grid_to_layer +
- * kib_fft_plan2d_exec + kib_layer_to_image). */
+ * the zero-padded layer:
+ *   kib_grid_to_image_columns  inverse DFT along the rows of the grid_size^2 grid, only
+ *                              for its non-zero columns -> scratch (size rows of
+ *                              grid_size complex values, row stride scratch_row_stride);
+ *   kib_grid_to_image_rows     one size-point inverse FFT per image row in shared memory
+ *                              with the layer_to_image arithmetic (see kib_layer_to_image)
+ *                              applied from registers; accumulates into image_plane.
+ * kib_grid_to_image runs both.  The reference's layer buffer is large enough as scratch.
+ * Single precision and size in {2048, 4096, 8192, 16384} only;
+ * kib_grid_to_image_supported returns 1 for supported combinations and 0 otherwise
+ * (callers then use kib_grid_to_layer + kib_fft_plan2d_exec + kib_layer_to_image). */
 int kib_grid_to_image_supported(int size, int grid_size, int dtype);
+int kib_grid_to_image_columns(void *scratch, int scratch_row_stride, int size,
+                              const void *grid_plane, int grid_row_stride, int grid_size,
+                              int dtype, kib_stream_t stream);
+int kib_grid_to_image_rows(void *image_plane, int image_row_stride,
+                           const void *scratch, int scratch_row_stride, int grid_size, int size,
+                           const void *kernel1d, double lm_scale, double lm_bias, double w,
+                           int dtype, kib_stream_t stream);
 int kib_grid_to_image(void *image_plane, int image_row_stride,
                       const void *grid_plane, int grid_row_stride, int grid_size,
                       void *scratch, int scratch_row_stride, int size,

@@ -69,6 +69,8 @@ SIGNATURES = {
     'kib_image_to_layer': [_vp, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
     'kib_grid_to_image': [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
     'kib_grid_to_image_supported': [_i, _i, _i],
+    'kib_grid_to_image_columns': [_vp, _i, _i, _vp, _i, _i, _i, _vp],
+    'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _i, _vp],
     'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
     'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
     'kib_apply_primary_beam': [_vp, _i, _i64, _vp, _i, _i, _i, _d, _d, _i, _vp],
@@ -142,7 +144,7 @@ _ONE_KERNEL = frozenset([
     'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
     'kib_abs_histogram', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
     'kib_density_weights', 'kib_fill', 'kib_predict', 'kib_fp32_peak_kernel',
-    'kib_unpack_records'])
+    'kib_unpack_records', 'kib_grid_to_image_columns', 'kib_grid_to_image_rows'])
 
 #: number of hand-written kernels launched through this module (cuFFT and memset/memcpy
 #: are not counted); bench.py reports the difference over its timed region

@@ -281,8 +281,8 @@ class GridToImage(accel.OperationSequence):
         super().__init__(command_queue, operations, compounds, allocator=allocator)
         self.slots['grid'] = accel.IOSlot(shape_grid, fft_plan.dtype_src)
         #: use the fused pruned transform (kib_grid_to_image) when the library supports
-        #: the size; off until it beats the pad + cuFFT + layer_to_image sequence
-        self.fused = False
+        #: the size (single precision, power-of-two images of 2048..16384 pixels)
+        self.fused = True
 
     def set_w(self, w):
         self._layer_to_image.set_w(w)
@@ -294,14 +294,18 @@ class GridToImage(accel.OperationSequence):
         image = self.buffer('image')
         kernel1d = self.buffer('kernel1d')
         image_plane = image.padded_shape[1] * image.padded_shape[2] * image.dtype.itemsize
+        dtype = _lib.dtype_code(grid.dtype)
+        stream = self.command_queue.stream
         for pol in range(polarizations):
-            with profile_device(self.command_queue, 'grid_to_image_fused'):
-                _lib.call('kib_grid_to_image',
+            with profile_device(self.command_queue, 'grid_to_image_columns'):
+                _lib.call('kib_grid_to_image_columns', layer.ptr, layer.padded_shape[1],
+                          layer.shape[1], (grid.ptr.value or 0) + pol * plane_bytes,
+                          grid.padded_shape[2], size, dtype, stream)
+            with profile_device(self.command_queue, 'grid_to_image_rows'):
+                _lib.call('kib_grid_to_image_rows',
                           (image.ptr.value or 0) + pol * image_plane, image.padded_shape[2],
-                          (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
-                          layer.ptr, layer.padded_shape[1], layer.shape[1], kernel1d.ptr,
-                          float(op.lm_scale), float(op.lm_bias), float(op.w),
-                          _lib.dtype_code(grid.dtype), self.command_queue.stream)
+                          layer.ptr, layer.padded_shape[1], size, layer.shape[1], kernel1d.ptr,
+                          float(op.lm_scale), float(op.lm_bias), float(op.w), dtype, stream)
 
     def _run(self):
         grid = self.buffer('grid')

@@ -154,12 +154,13 @@ def _fused_case(context, queue, pixels, grid_size, pols, seed, fused):
     return g2i, grid, kernel1d, lm_scale, lm_bias
 
 
-@pytest.mark.parametrize('pixels,grid_size,pols', [(1024, 616, 2), (1024, 1024, 1),
-                                                   (2048, 1230, 1), (1024, 30, 1)])
+@pytest.mark.parametrize('pixels,grid_size,pols', [(2048, 1230, 2), (2048, 2048, 1),
+                                                   (2048, 1234, 1), (2048, 30, 1),
+                                                   (4096, 2466, 1)])
 def test_grid_to_image_fused_vs_oracle(gpu, oracle, pixels, grid_size, pols):
     """The pruned, fused transform (kib_grid_to_image) against the oracle's
-    grid_to_image (numpy ifft2 in the reference's host arithmetic), including a grid
-    whose width is not a multiple of the 8-column block and a full-width grid.
+    grid_to_image (numpy ifft2 in the reference's host arithmetic), including grids
+    whose width is not a multiple of the 4-column block and a full-width grid.
     Bar: 1e-4 RMS relative to peak (north_star); observed ~3e-7."""
     context, queue = gpu
     from katsdpimager_b200 import _lib
