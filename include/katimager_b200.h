@@ -172,6 +172,10 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
  *   kib_grid_to_image_rows     one size-point inverse FFT per image row in shared memory
  *                              with the layer_to_image arithmetic (see kib_layer_to_image)
  *                              applied from registers; accumulates into image_plane.
+ *                              The per-pixel factor exp(2 pi i w (n-1)) n / (k1d[y] k1d[x])
+ *                              does not depend on the polarization: factor_mode 1 also
+ *                              stores it in `factors` (size x size complex, row stride
+ *                              size), 2 loads it from there, 0 ignores `factors`.
  * kib_grid_to_image runs both.  The reference's layer buffer is large enough as scratch.
  * Single precision and size in {2048, 4096, 8192, 16384} only;
  * kib_grid_to_image_supported returns 1 for supported combinations and 0 otherwise
@@ -183,7 +187,7 @@ int kib_grid_to_image_columns(void *scratch, int scratch_row_stride, int size,
 int kib_grid_to_image_rows(void *image_plane, int image_row_stride,
                            const void *scratch, int scratch_row_stride, int grid_size, int size,
                            const void *kernel1d, double lm_scale, double lm_bias, double w,
-                           int dtype, kib_stream_t stream);
+                           void *factors, int factor_mode, int dtype, kib_stream_t stream);
 int kib_grid_to_image(void *image_plane, int image_row_stride,
                       const void *grid_plane, int grid_row_stride, int grid_size,
                       void *scratch, int scratch_row_stride, int size,

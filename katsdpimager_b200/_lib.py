@@ -70,7 +70,7 @@ SIGNATURES = {
     'kib_grid_to_image': [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
     'kib_grid_to_image_supported': [_i, _i, _i],
     'kib_grid_to_image_columns': [_vp, _i, _i, _vp, _i, _i, _i, _vp],
-    'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _i, _vp],
+    'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
     'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
     'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
     'kib_apply_primary_beam': [_vp, _i, _i64, _vp, _i, _i, _i, _d, _d, _i, _vp],

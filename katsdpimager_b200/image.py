@@ -283,6 +283,7 @@ class GridToImage(accel.OperationSequence):
         #: use the fused pruned transform (kib_grid_to_image) when the library supports
         #: the size (single precision, power-of-two images of 2048..16384 pixels)
         self.fused = True
+        self._factors = None
 
     def set_w(self, w):
         self._layer_to_image.set_w(w)
@@ -296,6 +297,14 @@ class GridToImage(accel.OperationSequence):
         image_plane = image.padded_shape[1] * image.padded_shape[2] * image.dtype.itemsize
         dtype = _lib.dtype_code(grid.dtype)
         stream = self.command_queue.stream
+        n = layer.shape[1]
+        factors = None
+        if polarizations > 1:
+            # the W rotation / n / taper factor of every pixel is computed for the first
+            # polarization, kept, and reused by the others
+            if self._factors is None or self._factors.shape != (n, n):
+                self._factors = accel.DeviceArray(self.command_queue.context, (n, n), grid.dtype)
+            factors = self._factors.ptr
         for pol in range(polarizations):
             with profile_device(self.command_queue, 'grid_to_image_columns'):
                 _lib.call('kib_grid_to_image_columns', layer.ptr, layer.padded_shape[1],
@@ -305,7 +314,8 @@ class GridToImage(accel.OperationSequence):
                 _lib.call('kib_grid_to_image_rows',
                           (image.ptr.value or 0) + pol * image_plane, image.padded_shape[2],
                           layer.ptr, layer.padded_shape[1], size, layer.shape[1], kernel1d.ptr,
-                          float(op.lm_scale), float(op.lm_bias), float(op.w), dtype, stream)
+                          float(op.lm_scale), float(op.lm_bias), float(op.w),
+                          factors, 0 if factors is None else (1 if pol == 0 else 2), dtype, stream)
 
     def _run(self):
         grid = self.buffer('grid')
