@@ -185,6 +185,39 @@ def test_grid_to_image_fused_vs_oracle(gpu, oracle, pixels, grid_size, pols):
     np.testing.assert_allclose(g2i.buffer('image').get(queue), 2 * actual, rtol=1e-5, atol=1e-3)
 
 
+def test_grid_to_image_fused_padded_buffers(gpu, oracle):
+    """The fused transform honours row strides: image, layer (scratch) and grid buffers with
+    padded rows give the same image as tightly packed ones."""
+    context, queue = gpu
+    pixels, grid_size, pols = 2048, 1226, 2
+    g2i, grid, kernel1d, lm_scale, lm_bias = _fused_case(
+        context, queue, pixels, grid_size, pols, 13, True)
+    g2i.set_w(12.25)
+    g2i.buffer('image').zero(queue)
+    g2i()
+    packed = g2i.buffer('image').get(queue)
+    padded = {
+        'image': accel.DeviceArray(context, (pols, pixels, pixels), np.float32,
+                                   (pols, pixels, pixels + 16)),
+        'layer': accel.DeviceArray(context, (pixels, pixels), np.complex64,
+                                   (pixels, pixels + 16)),
+        'grid': accel.DeviceArray(context, (pols, grid_size, grid_size), np.complex64,
+                                  (pols, grid_size + 2, grid_size + 6)),
+    }
+    template = image.GridImageTemplate(context, np.float32)
+    plan = template.make_fft_plan((pixels, pixels), (pixels, pixels + 16))
+    other = template.instantiate_grid_to_image(queue, (pols, grid_size, grid_size),
+                                               lm_scale, lm_bias, plan)
+    other.bind(**padded)
+    other.ensure_all_bound()
+    other.buffer('grid').set(queue, grid)
+    other.buffer('kernel1d').set(queue, kernel1d)
+    other.buffer('image').zero(queue)
+    other.set_w(12.25)
+    other()
+    np.testing.assert_array_equal(other.buffer('image').get(queue), packed)
+
+
 @pytest.mark.parametrize('pixels,grid_size', [(4096, 2470), (8192, 4940), (16384, 1000)])
 def test_grid_to_image_fused_vs_cufft(gpu, pixels, grid_size):
     """Full-size planes: the fused transform against the pad + cuFFT + layer_to_image
