@@ -5,14 +5,18 @@
 
 One *step* = one dirty-image pass over one synthetic MeerKAT channel at BASELINE
 config 2 (8192^2 image, 4 polarizations, 16 W slices, 7x7 support x 8 oversample):
-for every W slice { clear grid, grid the slice's visibilities, pad + ifftshift + cuFFT +
-taper/W-term epilogue for 4 polarizations }.  With N > 1 every rank images its own
-channel on its own GPU (weak scaling, no collective on the data path).
+for every W slice { clear grid, grid the slice's visibilities, grid -> image for the 4
+polarizations (fused pruned transform: column pass + row pass with the taper / W-term
+epilogue) }.  With N > 1 every rank images its own channel on its own GPU (weak scaling, no
+collective on the data path).
 
 `value`  = visibilities gridded per second over the whole step with inputs resident in HBM.
 `e2e`    = the same metric through the Imaging facade with HOST buffers: per 1 Mi-visibility
-           chunk set_coordinates/set_vis (pinned staging + H2D) + grid, and a D2H read of
-           the dirty image, all inside the timed region.
+           chunk set_coordinates/set_vis (H2D of pinned records) + grid, and a D2H read of
+           the dirty image, all inside the timed region; a few imagers on their own command
+           queues take channels in turn so that copies overlap kernels (ImagingPipeline).
+`roofline` = the kernel that takes most of the step (row pass of the fused transform, HBM
+           roofline over its algorithmic bytes); `roofline_columns`, `roofline_gridder` follow.
 `--impl reference` times the CPU oracle (port of the reference's --host path) on a bounded
 sample of the same workload with all host threads.
 """
