@@ -168,7 +168,10 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
  * the zero-padded layer:
  *   kib_grid_to_image_columns  inverse DFT along the rows of the grid_size^2 grid, only
  *                              for its non-zero columns -> scratch (size rows of
- *                              grid_size complex values, row stride scratch_row_stride);
+ *                              grid_size complex values, row stride scratch_row_stride).
+ *                              Two kernels: a decimation-in-frequency fold of the grid
+ *                              into fold_scratch (kib_grid_to_image_fold_bytes bytes),
+ *                              then the sub-transforms of its 64 KB tiles;
  *   kib_grid_to_image_rows     one size-point inverse FFT per image row in shared memory
  *                              with the layer_to_image arithmetic (see kib_layer_to_image)
  *                              applied from registers; accumulates into image_plane.
@@ -176,21 +179,22 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
  *                              does not depend on the polarization: factor_mode 1 also
  *                              stores it in `factors` (size x size complex, row stride
  *                              size), 2 loads it from there, 0 ignores `factors`.
- * kib_grid_to_image runs both.  The reference's layer buffer is large enough as scratch.
- * Single precision and size in {2048, 4096, 8192, 16384} only;
+ * kib_grid_to_image runs both (factor_mode 0).  The reference's layer buffer is large
+ * enough as scratch.  Single precision and size in {2048, 4096, 8192, 16384} only;
  * kib_grid_to_image_supported returns 1 for supported combinations and 0 otherwise
  * (callers then use kib_grid_to_layer + kib_fft_plan2d_exec + kib_layer_to_image). */
 int kib_grid_to_image_supported(int size, int grid_size, int dtype);
+int kib_grid_to_image_fold_bytes(int size, int grid_size, int64_t *bytes);
 int kib_grid_to_image_columns(void *scratch, int scratch_row_stride, int size,
                               const void *grid_plane, int grid_row_stride, int grid_size,
-                              int dtype, kib_stream_t stream);
+                              void *fold_scratch, int dtype, kib_stream_t stream);
 int kib_grid_to_image_rows(void *image_plane, int image_row_stride,
                            const void *scratch, int scratch_row_stride, int grid_size, int size,
                            const void *kernel1d, double lm_scale, double lm_bias, double w,
                            void *factors, int factor_mode, int dtype, kib_stream_t stream);
 int kib_grid_to_image(void *image_plane, int image_row_stride,
                       const void *grid_plane, int grid_row_stride, int grid_size,
-                      void *scratch, int scratch_row_stride, int size,
+                      void *scratch, int scratch_row_stride, void *fold_scratch, int size,
                       const void *kernel1d, double lm_scale, double lm_bias, double w,
                       int dtype, kib_stream_t stream);
 /* kib_image_to_layer replaces image_to_layer.mako (oracle image.py:836-843):

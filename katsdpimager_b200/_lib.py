@@ -67,9 +67,10 @@ SIGNATURES = {
     'kib_layer_to_grid': [_vp, _i, _i, _vp, _i, _i, _i, _vp],
     'kib_layer_to_image': [_vp, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
     'kib_image_to_layer': [_vp, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
-    'kib_grid_to_image': [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _d, _d, _d, _i, _vp],
+    'kib_grid_to_image': [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _d, _d, _d, _i, _vp],
     'kib_grid_to_image_supported': [_i, _i, _i],
-    'kib_grid_to_image_columns': [_vp, _i, _i, _vp, _i, _i, _i, _vp],
+    'kib_grid_to_image_columns': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
+    'kib_grid_to_image_fold_bytes': [_i, _i, POINTER(c_int64)],
     'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
     'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
     'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
@@ -144,7 +145,7 @@ _ONE_KERNEL = frozenset([
     'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
     'kib_abs_histogram', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
     'kib_density_weights', 'kib_fill', 'kib_predict', 'kib_fp32_peak_kernel',
-    'kib_unpack_records', 'kib_grid_to_image_columns', 'kib_grid_to_image_rows'])
+    'kib_unpack_records', 'kib_grid_to_image_rows'])
 
 #: number of hand-written kernels launched through this module (cuFFT and memset/memcpy
 #: are not counted); bench.py reports the difference over its timed region
@@ -157,10 +158,19 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
     if name in _ONE_KERNEL:
         kernel_launches += 1
+    elif name == 'kib_grid_to_image_columns':
+        kernel_launches += 2                 # fold + column transforms
     elif name == 'kib_grid_to_image':
-        kernel_launches += 2                 # column pass + row pass
+        kernel_launches += 3                 # fold + column transforms + row pass
     elif name == 'kib_clean_minor_cycles':
         kernel_launches += int(args[26])     # one launch per requested cycle
+
+
+def grid_to_image_fold_bytes(size, grid_size):
+    """Bytes of fold scratch kib_grid_to_image_columns needs."""
+    nbytes = c_int64()
+    call('kib_grid_to_image_fold_bytes', int(size), int(grid_size), ctypes.byref(nbytes))
+    return int(nbytes.value)
 
 
 def grid_to_image_supported(size, grid_size, dtype):

@@ -284,6 +284,7 @@ class GridToImage(accel.OperationSequence):
         #: the size (single precision, power-of-two images of 2048..16384 pixels)
         self.fused = True
         self._factors = None
+        self._fold = None
 
     def set_w(self, w):
         self._layer_to_image.set_w(w)
@@ -305,11 +306,14 @@ class GridToImage(accel.OperationSequence):
             if self._factors is None or self._factors.shape != (n, n):
                 self._factors = accel.DeviceArray(self.command_queue.context, (n, n), grid.dtype)
             factors = self._factors.ptr
+        fold_bytes = _lib.grid_to_image_fold_bytes(n, size)
+        if self._fold is None or self._fold.shape[0] < fold_bytes:
+            self._fold = accel.DeviceArray(self.command_queue.context, (fold_bytes,), np.uint8)
         for pol in range(polarizations):
             with profile_device(self.command_queue, 'grid_to_image_columns'):
                 _lib.call('kib_grid_to_image_columns', layer.ptr, layer.padded_shape[1],
                           layer.shape[1], (grid.ptr.value or 0) + pol * plane_bytes,
-                          grid.padded_shape[2], size, dtype, stream)
+                          grid.padded_shape[2], size, self._fold.ptr, dtype, stream)
             with profile_device(self.command_queue, 'grid_to_image_rows'):
                 _lib.call('kib_grid_to_image_rows',
                           (image.ptr.value or 0) + pol * image_plane, image.padded_shape[2],
