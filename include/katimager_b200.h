@@ -197,6 +197,28 @@ int kib_grid_to_image(void *image_plane, int image_row_stride,
                       void *scratch, int scratch_row_stride, void *fold_scratch, int size,
                       const void *kernel1d, double lm_scale, double lm_bias, double w,
                       int dtype, kib_stream_t stream);
+/* kib_image_to_grid_rows + kib_image_to_grid_columns replace the per-polarization body of
+ * ImageToGrid._run (image.py:716-740: image_to_layer.mako, the forward cuFFT and the four
+ * fftshift copies of the centre of the layer into the grid) by the mirror image of the
+ * transform above, with the same restrictions (kib_grid_to_image_supported):
+ *   kib_image_to_grid_rows     image row -> image_to_layer arithmetic (see
+ *                              kib_image_to_layer) -> forward size-point FFT in shared
+ *                              memory -> the grid_size columns the grid keeps -> scratch
+ *                              (size rows of grid_size complex values).  factor_mode as in
+ *                              kib_grid_to_image_rows (the factor here is
+ *                              exp(-2 pi i w (n-1)) / (k1d[y] k1d[x] n));
+ *   kib_image_to_grid_columns  forward DFT along the rows of scratch, only for the
+ *                              grid_size output rows the grid keeps -> grid_plane
+ *                              (tile transforms into fold_scratch, then one butterfly
+ *                              per output element). */
+int kib_image_to_grid_rows(void *scratch, int scratch_row_stride, int grid_size, int size,
+                           const void *image_plane, int image_row_stride,
+                           const void *kernel1d, double lm_scale, double lm_bias, double w,
+                           void *factors, int factor_mode, int dtype, kib_stream_t stream);
+int kib_image_to_grid_columns(void *grid_plane, int grid_row_stride, int grid_size,
+                              const void *scratch, int scratch_row_stride, int size,
+                              void *fold_scratch, int dtype, kib_stream_t stream);
+
 /* kib_image_to_layer replaces image_to_layer.mako (oracle image.py:836-843):
  *   layer[ifftshift(y,x)] = image[y][x] / (kernel1d[y]*kernel1d[x]*n) * exp(-2 pi i w (n-1)) */
 int kib_image_to_layer(void *layer, int layer_row_stride,

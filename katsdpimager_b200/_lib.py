@@ -71,6 +71,8 @@ SIGNATURES = {
     'kib_grid_to_image_supported': [_i, _i, _i],
     'kib_grid_to_image_columns': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_grid_to_image_fold_bytes': [_i, _i, POINTER(c_int64)],
+    'kib_image_to_grid_rows': [_vp, _i, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
+    'kib_image_to_grid_columns': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
     'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
     'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
@@ -145,7 +147,7 @@ _ONE_KERNEL = frozenset([
     'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
     'kib_abs_histogram', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
     'kib_density_weights', 'kib_fill', 'kib_predict', 'kib_fp32_peak_kernel',
-    'kib_unpack_records', 'kib_grid_to_image_rows'])
+    'kib_unpack_records', 'kib_grid_to_image_rows', 'kib_image_to_grid_rows'])
 
 #: number of hand-written kernels launched through this module (cuFFT and memset/memcpy
 #: are not counted); bench.py reports the difference over its timed region
@@ -158,8 +160,8 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
     if name in _ONE_KERNEL:
         kernel_launches += 1
-    elif name == 'kib_grid_to_image_columns':
-        kernel_launches += 2                 # fold + column transforms
+    elif name in ('kib_grid_to_image_columns', 'kib_image_to_grid_columns'):
+        kernel_launches += 2                 # fold / unfold + column transforms
     elif name == 'kib_grid_to_image':
         kernel_launches += 3                 # fold + column transforms + row pass
     elif name == 'kib_clean_minor_cycles':

@@ -356,15 +356,51 @@ class ImageToGrid(accel.OperationSequence):
         }
         super().__init__(command_queue, operations, compounds, allocator=allocator)
         self.slots['grid'] = accel.IOSlot(shape_grid, fft_plan.dtype_dest)
+        #: use the fused pruned transform when the library supports the size
+        self.fused = True
+        self._factors = None
+        self._fold = None
 
     def set_w(self, w):
         self._image_to_layer.set_w(w)
+
+    def _run_fused(self, grid, layer, polarizations, size, plane_bytes):
+        """Mirror image of :meth:`GridToImage._run_fused` (csrc/kib_gridfft.cu)."""
+        op = self._image_to_layer
+        image = self.buffer('image')
+        kernel1d = self.buffer('kernel1d')
+        image_plane = image.padded_shape[1] * image.padded_shape[2] * image.dtype.itemsize
+        dtype = _lib.dtype_code(grid.dtype)
+        stream = self.command_queue.stream
+        n = layer.shape[1]
+        context = self.command_queue.context
+        factors = None
+        if polarizations > 1:
+            if self._factors is None or self._factors.shape != (n, n):
+                self._factors = accel.DeviceArray(context, (n, n), grid.dtype)
+            factors = self._factors.ptr
+        fold_bytes = _lib.grid_to_image_fold_bytes(n, size)
+        if self._fold is None or self._fold.shape[0] < fold_bytes:
+            self._fold = accel.DeviceArray(context, (fold_bytes,), np.uint8)
+        for pol in range(polarizations):
+            with profile_device(self.command_queue, 'image_to_grid_rows'):
+                _lib.call('kib_image_to_grid_rows', layer.ptr, layer.padded_shape[1], size, n,
+                          (image.ptr.value or 0) + pol * image_plane, image.padded_shape[2],
+                          kernel1d.ptr, float(op.lm_scale), float(op.lm_bias), float(op.w),
+                          factors, 0 if factors is None else (1 if pol == 0 else 2), dtype, stream)
+            with profile_device(self.command_queue, 'image_to_grid_columns'):
+                _lib.call('kib_image_to_grid_columns',
+                          (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
+                          layer.ptr, layer.padded_shape[1], n, self._fold.ptr, dtype, stream)
 
     def _run(self):
         grid = self.buffer('grid')
         layer = self.buffer('layer')
         polarizations, size = _check_grid(grid, layer)
         plane_bytes = grid.padded_shape[1] * grid.padded_shape[2] * grid.dtype.itemsize
+        if self.fused and _lib.grid_to_image_supported(layer.shape[1], size, grid.dtype):
+            self._run_fused(grid, layer, polarizations, size, plane_bytes)
+            return
         for pol in range(polarizations):
             self._image_to_layer.set_polarization(pol)
             super()._run()
