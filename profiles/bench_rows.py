@@ -106,7 +106,7 @@ def main():
          algorithmic_gb=(8 * size * size + 16 * N * size + 8 * N * N) / 1e9,
          note='cuFFT route (pad/shift + cuFFT + epilogue): 0.87 ms, 3.95 GB')
     seconds = timed(queue, i2g)
-    emit(row='image_to_grid', config='8192^2, 1 polarization (prologue + cuFFT + crop/shift)',
+    emit(row='image_to_grid', config='8192^2, 1 polarization (fused pruned transform: row pass + tile transforms + unfold)',
          ms=seconds * 1e3, planes_per_s=1 / seconds)
 
     # ------------------------------------------------------------ CLEAN (config 5 geometry)
