@@ -193,3 +193,34 @@ def test_imaging_pipeline_matches_single_imager(gpu):
     assert _rms_rel(got[3.0], expected[1.0]) > 0.05
     with pytest.raises(ValueError):
         imaging.ImagingPipeline(template, 0, ip, gp, 1024, 0, 2)
+
+
+def test_imaging_fused_routes_match_cufft_routes(gpu):
+    """A whole process_channel replay (PSF, dirty image, CLEAN, model -> grid -> degrid,
+    residual) at 2048^2, where the fused pruned transforms are taken, against the same replay
+    with the pad + cuFFT + epilogue routes that the golden files pin at small sizes."""
+    context, queue = gpu
+    fx = cases.imaging_case(pixels=2048, num_baselines=60, num_dumps=40)
+    ip, gp, cp = fx['image_parameters'], fx['grid_parameters'], fx['clean_parameters']
+    wp = prm.WeightParameters(weight.WeightType.UNIFORM)
+    template = imaging.ImagingTemplate(context, fx['array_parameters'], ip.fixed, wp, gp.fixed, cp)
+    outputs = {}
+    for fused in (True, False):
+        def make():
+            imager = template.instantiate(queue, ip, gp, fx['vis_block'], 0, fx['major'])
+            assert imager._grid_to_image.fused and imager._image_to_grid.fused
+            imager._grid_to_image.fused = fused
+            imager._image_to_grid.fused = fused
+            return imager
+        outputs[fused] = cases.run_imaging(make, fx, clean_batch=16)
+    a, b = outputs[True], outputs[False]
+    np.testing.assert_array_equal(a['psf_patch'], b['psf_patch'])
+    np.testing.assert_allclose(a['psf_peak'], b['psf_peak'], rtol=1e-5)
+    for name in ('psf', 'dirty0', 'residual'):
+        assert _rms_rel(a[name], b[name]) < 2e-5, name
+    np.testing.assert_allclose(a['noise'], b['noise'], rtol=1e-4)
+    # the same components: CLEAN is bit exact on identical inputs, and the two routes differ by
+    # rounding only, which may reorder near-equal peaks but not the set of pixels found
+    assert len(a['values']) == len(b['values'])
+    np.testing.assert_array_equal(np.argwhere(a['model'] != 0), np.argwhere(b['model'] != 0))
+    np.testing.assert_allclose(a['model'], b['model'], rtol=0, atol=1e-4 * np.abs(b['model']).max())
