@@ -94,7 +94,8 @@ class ClockSampler:
     NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, device):
-        self.samples = []
+        self.samples = []           # (arrival time, fields)
+        self.window = [None, None]  # wall-clock bounds of the timed region
         self.proc = None
         try:
             self.proc = subprocess.Popen(
@@ -110,7 +111,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             fields = [f.strip() for f in line.split(',')]
             if len(fields) >= 7:
-                self.samples.append(fields)
+                self.samples.append((time.monotonic(), fields))
+
+    def mark_start(self):
+        self.window[0] = time.monotonic()
+
+    def mark_stop(self):
+        self.window[1] = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -121,7 +128,17 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         clocks, reasons, sm_max, power = [], set(), None, []
-        for f in self.samples:
+        lo, hi = self.window
+        inside = [f for t, f in self.samples
+                  if (lo is None or t >= lo) and (hi is None or t <= hi + 0.06)]
+        # nvidia-smi needs a few hundred ms per sample when several ranks query at once: if no
+        # sample fell inside a short timed region, use those taken under the same load just
+        # before it (warm-up steps) and say so
+        note = None
+        if not inside and self.samples:
+            inside = [f for _, f in self.samples[-3:]]
+            note = 'no sample inside the timed region; last samples of the warm-up used'
+        for f in inside:
             try:
                 clocks.append(float(f[0]))
                 sm_max = float(f[1])
@@ -131,9 +148,12 @@ class ClockSampler:
             for name, value in zip(self.NAMES, f[3:7]):
                 if value.lower().startswith('active'):
                     reasons.add(name)
-        return {'sm_mhz': float(np.median(clocks)) if clocks else None, 'sm_max_mhz': sm_max,
-                'power_w_max': max(power) if power else None, 'samples': len(clocks),
-                'reasons': sorted(reasons)}
+        result = {'sm_mhz': float(np.median(clocks)) if clocks else None, 'sm_max_mhz': sm_max,
+                  'power_w_max': max(power) if power else None, 'samples': len(clocks),
+                  'reasons': sorted(reasons)}
+        if note:
+            result['note'] = note
+        return result
 
 
 # --------------------------------------------------------------------------- distributed
@@ -375,11 +395,12 @@ def run_gpu(args, ranks):
     fp32_peak = max(peaks)
 
     # ---- timed region: K steps with resident inputs
+    sampler = ClockSampler(ranks.local_rank)        # already streaming when the timed region starts
     for _ in range(args.warmup):
         step_resident()
     queue.finish()
     ranks.barrier()
-    sampler = ClockSampler(ranks.local_rank)
+    sampler.mark_start()
     timer = profiling.DeviceTimer()
     profiling.set_timer(timer)
     launches0 = _lib.kernel_launches
@@ -389,6 +410,7 @@ def run_gpu(args, ranks):
     stop = queue.enqueue_marker()
     stop.wait()
     queue.finish()
+    sampler.mark_stop()
     seconds = stop.time_since(start)
     launches = _lib.kernel_launches - launches0
     profiling.set_timer(None)
