@@ -786,7 +786,7 @@ static bool config_allowed(int mx, int my, int P, int dtype)
     return mx * my * P * 2 * (dtype == KIB_F64 ? 2 : 1) <= GRID_ACC_BUDGET;
 }
 
-static bool choose_config(int K, int P, int dtype, GridConfig *out)
+__attribute__((unused)) static bool choose_config(int K, int P, int dtype, GridConfig *out)
 {
     double best_score = 1e30;
     bool found = false;
@@ -1032,8 +1032,29 @@ static int dispatch_pols(GridParams &prm, const GridConfig &cfg, int P, int dtyp
     return -1;
 }
 
+// The file is compiled twice (Makefile: -DKIB_GRID_PART=1 single precision + entry point,
+// -DKIB_GRID_PART=2 double precision) so that the two sets of kernel instantiations build in
+// parallel.
+#ifndef KIB_GRID_PART
+#define KIB_GRID_PART 1
+#endif
+int grid_dispatch_f32(GridParams &prm, const GridConfig &cfg, int P, cudaStream_t stream);
+int grid_dispatch_f64(GridParams &prm, const GridConfig &cfg, int P, cudaStream_t stream);
+#if KIB_GRID_PART == 1
+int grid_dispatch_f32(GridParams &prm, const GridConfig &cfg, int P, cudaStream_t stream)
+{
+    return dispatch_pols<float>(prm, cfg, P, KIB_F32, stream);
+}
+#else
+int grid_dispatch_f64(GridParams &prm, const GridConfig &cfg, int P, cudaStream_t stream)
+{
+    return dispatch_pols<double>(prm, cfg, P, KIB_F64, stream);
+}
+#endif
+
 }  // namespace kib
 
+#if KIB_GRID_PART == 1
 using namespace kib;
 
 extern "C" int kib_grid(void *grid, int grid_row_stride, int64_t grid_pol_stride, int grid_size,
@@ -1086,6 +1107,7 @@ extern "C" int kib_grid(void *grid, int grid_row_stride, int64_t grid_pol_stride
     prm.magic_x = (unsigned) ((1ull << 32) / prm.bx) + 1;
     prm.magic_y = (unsigned) ((1ull << 32) / prm.by) + 1;
     cudaStream_t s = as_stream(stream);
-    if (dtype == KIB_F32) return dispatch_pols<float>(prm, cfg, num_pols, dtype, s);
-    return dispatch_pols<double>(prm, cfg, num_pols, dtype, s);
+    if (dtype == KIB_F32) return grid_dispatch_f32(prm, cfg, num_pols, s);
+    return grid_dispatch_f64(prm, cfg, num_pols, s);
 }
+#endif  // KIB_GRID_PART == 1
