@@ -279,6 +279,12 @@ clean_step_kernel(const CleanStepParams prm)
     __shared__ Best<Real> scratch[33];
     __shared__ int is_last;
     int *state = prm.state;
+    // Programmatic dependent launch: consecutive cycles are launched with stream serialization
+    // relaxed, so this grid may already be resident while the previous cycle finishes.  Wait
+    // for its completion (and the visibility of its writes) before touching any state, then
+    // let the next cycle's blocks be scheduled behind this one.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     // Uniform across the grid: state[1] is only ever written by launches in which every
     // block takes the "below threshold" exit.
     if (__ldcg(state + 1) != 0) return;
@@ -512,10 +518,21 @@ rank_kernel(const Real *__restrict__ image, int row_stride, long long pol_stride
 template <typename Real, int P>
 static void launch_step_mode(const CleanStepParams &prm, int mode, dim3 grid, cudaStream_t stream)
 {
+    // programmatic stream serialization: see the top of clean_step_kernel
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t config = {};
+    config.gridDim = grid;
+    config.blockDim = dim3(CLEAN_THREADS);
+    config.dynamicSmemBytes = 0;
+    config.stream = stream;
+    config.attrs = &attr;
+    config.numAttrs = 1;
     if (mode == KIB_CLEAN_I)
-        clean_step_kernel<Real, P, KIB_CLEAN_I><<<grid, CLEAN_THREADS, 0, stream>>>(prm);
+        cudaLaunchKernelEx(&config, clean_step_kernel<Real, P, KIB_CLEAN_I>, prm);
     else
-        clean_step_kernel<Real, P, KIB_CLEAN_SUMSQ><<<grid, CLEAN_THREADS, 0, stream>>>(prm);
+        cudaLaunchKernelEx(&config, clean_step_kernel<Real, P, KIB_CLEAN_SUMSQ>, prm);
 }
 
 template <typename Real>
