@@ -185,6 +185,53 @@ def test_grid_to_image_fused_vs_oracle(gpu, oracle, pixels, grid_size, pols):
     np.testing.assert_allclose(g2i.buffer('image').get(queue), 2 * actual, rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize('pixels,grid_size', [(8192, 4940), (16384, 9864)])
+def test_grid_to_image_fused_impulses(gpu, pixels, grid_size):
+    """Full BASELINE sizes, analytic answer: a few non-zero grid cells give a sum of plane
+    waves, image[y][x] = sum_k Re(a_k exp(2 pi i (u_k x + v_k y) / N)) n / (k1d[y] k1d[x])
+    at w = 0 (x, y and u, v counted from the image / grid centre).  Checked on sampled rows in
+    float64; independent of cuFFT and of the oracle."""
+    context, queue = gpu
+    rs = RandomState(31)
+    lm_scale = 0.2 / pixels
+    lm_bias = -lm_scale * pixels / 2
+    template = image.GridImageTemplate(context, np.float32)
+    plan = template.make_fft_plan((pixels, pixels), (pixels, pixels))
+    g2i = template.instantiate_grid_to_image(queue, (1, grid_size, grid_size),
+                                             lm_scale, lm_bias, plan)
+    assert g2i.fused
+    g2i.ensure_all_bound()
+    half = grid_size // 2
+    cells = [(0, 0), (half - 1, half - 1), (-half, -half), (37, -1201), (-half, half - 1),
+             (1, 0), (0, -1), (-777, 2048)]
+    amps = rs.complex_normal(0.0j, 1.0, len(cells)).astype(np.complex64)
+    grid = np.zeros((1, grid_size, grid_size), np.complex64)
+    for (v, u), a in zip(cells, amps):
+        grid[0, v + half, u + half] += a
+    kernel1d = rs.uniform(1.0, 2.0, pixels).astype(np.float32)
+    g2i.buffer('grid').set(queue, grid)
+    g2i.buffer('kernel1d').set(queue, kernel1d)
+    g2i.buffer('image').zero(queue)
+    g2i.set_w(0.0)
+    g2i()
+    actual = g2i.buffer('image').get(queue)[0]
+    rows = np.unique(np.concatenate(([0, 1, pixels // 2 - 1, pixels // 2, pixels - 1],
+                                     rs.randint(0, pixels, 40))))
+    x = np.arange(pixels, dtype=np.float64) - pixels // 2
+    lm = (np.arange(pixels).astype(np.float32) * np.float32(lm_scale) + np.float32(lm_bias))
+    lm2 = (lm * lm).astype(np.float64)
+    worst = 0.0
+    for yi in rows:
+        y = float(yi - pixels // 2)
+        value = np.zeros(pixels, np.complex128)
+        for (v, u), a in zip(cells, amps):
+            value += complex(a) * np.exp(2j * np.pi * (u * x + v * y) / pixels)
+        n = np.sqrt(1.0 - (lm2[yi] + lm2))
+        expected = value.real * n / (float(kernel1d[yi]) * kernel1d.astype(np.float64))
+        worst = max(worst, float(np.abs(actual[yi] - expected).max()))
+    assert worst < 2e-5 * np.abs(amps).sum()
+
+
 def test_grid_to_image_fused_padded_buffers(gpu, oracle):
     """The fused transform honours row strides: image, layer (scratch) and grid buffers with
     padded rows give the same image as tightly packed ones."""
@@ -298,6 +345,52 @@ def test_image_to_grid_fused_vs_cufft(gpu, pixels, grid_size):
     scale = np.abs(plain).max()
     assert np.sqrt(np.mean(np.abs(fused - plain) ** 2)) / scale < 2e-6
     assert np.abs(fused - plain).max() / scale < 2e-5
+
+
+@pytest.mark.parametrize('pixels,grid_size', [(8192, 4940), (16384, 9864)])
+def test_image_to_grid_fused_impulses(gpu, pixels, grid_size):
+    """Full BASELINE sizes, analytic answer: a few non-zero pixels give
+    grid[v][u] = sum_k f_k / (k1d[y_k] k1d[x_k] n_k) exp(-2 pi i (u x_k + v y_k) / N) at w = 0
+    (coordinates counted from the centres).  Checked on sampled grid rows in float64."""
+    context, queue = gpu
+    rs = RandomState(32)
+    lm_scale = 0.2 / pixels
+    lm_bias = -lm_scale * pixels / 2
+    template = image.GridImageTemplate(context, np.float32)
+    plan = template.make_fft_plan((pixels, pixels), (pixels, pixels))
+    i2g = template.instantiate_image_to_grid(queue, (1, grid_size, grid_size),
+                                             lm_scale, lm_bias, plan)
+    assert i2g.fused
+    i2g.ensure_all_bound()
+    mid = pixels // 2
+    pix = [(0, 0), (mid - 1, mid - 1), (-mid, -mid), (1234, -77), (-mid, mid - 1), (0, 1)]
+    flux = rs.uniform(0.5, 2.0, len(pix))
+    model = np.zeros((1, pixels, pixels), np.float32)
+    for (y, x), f in zip(pix, flux):
+        model[0, y + mid, x + mid] = f
+    kernel1d = rs.uniform(1.0, 2.0, pixels).astype(np.float32)
+    i2g.buffer('image').set(queue, model)
+    i2g.buffer('kernel1d').set(queue, kernel1d)
+    i2g.set_w(0.0)
+    i2g()
+    actual = i2g.buffer('grid').get(queue)[0]
+    half = grid_size // 2
+    lm = (np.arange(pixels).astype(np.float32) * np.float32(lm_scale) + np.float32(lm_bias))
+    lm2 = (lm * lm).astype(np.float64)
+    u = np.arange(grid_size, dtype=np.float64) - half
+    rows = np.unique(np.concatenate(([0, 1, half - 1, half, grid_size - 1],
+                                     rs.randint(0, grid_size, 40))))
+    worst = 0.0
+    for gy in rows:
+        v = float(gy - half)
+        expected = np.zeros(grid_size, np.complex128)
+        for (y, x), f in zip(pix, flux):
+            yi, xi = y + mid, x + mid
+            n = np.sqrt(1.0 - (lm2[yi] + lm2[xi]))
+            amp = float(np.float32(f)) / (float(kernel1d[yi]) * float(kernel1d[xi]) * n)
+            expected += amp * np.exp(-2j * np.pi * (u * x + v * y) / pixels)
+        worst = max(worst, float(np.abs(actual[gy] - expected).max()))
+    assert worst < 2e-5 * flux.sum()
 
 
 def test_scale(gpu):
