@@ -382,7 +382,6 @@ clean_step_kernel(const CleanStepParams prm)
             model[c] = add_rn_(model[c], scale[p]);
             vals[1 + p] = scale[p];
         }
-        state[0] = done + 1;
     }
     // Last block to finish selects the next peak.
     __syncthreads();
@@ -430,6 +429,10 @@ clean_step_kernel(const CleanStepParams prm)
             for (int p = 0; p < P; p++)
                 peak_pixel[p] = __ldcg(dirty + p * prm.pol_stride
                                        + (long long) pos.x * prm.row_stride + pos.y);
+            // The cycle count is published only here, after every block of this launch has
+            // taken its ticket: a block that starts late must still see `done`, not done + 1
+            // (it would skip its share of the subtraction on the last cycle of a batch).
+            state[0] = done + 1;
             state[2] = 0;
         }
     }

@@ -265,7 +265,8 @@ def test_grid_to_image_fused_padded_buffers(gpu, oracle):
     np.testing.assert_array_equal(other.buffer('image').get(queue), packed)
 
 
-@pytest.mark.parametrize('pixels,grid_size', [(4096, 2470), (8192, 4940), (16384, 1000)])
+@pytest.mark.parametrize('pixels,grid_size', [(4096, 2470), (8192, 4940), (16384, 1000),
+                                              (16384, 9864)])
 def test_grid_to_image_fused_vs_cufft(gpu, pixels, grid_size):
     """Full-size planes: the fused transform against the pad + cuFFT + layer_to_image
     sequence on the same random grid."""
