@@ -169,9 +169,11 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
  *   kib_grid_to_image_columns  inverse DFT along the rows of the grid_size^2 grid, only
  *                              for its non-zero columns -> scratch (size rows of
  *                              grid_size complex values, row stride scratch_row_stride).
- *                              Two kernels: a decimation-in-frequency fold of the grid
- *                              into fold_scratch (kib_grid_to_image_fold_bytes bytes),
- *                              then the sub-transforms of its 64 KB tiles;
+ *                              A decimation-in-frequency fold of the grid followed by the
+ *                              sub-transforms of its 64 KB tiles: one cluster kernel that
+ *                              exchanges the fold through distributed shared memory for
+ *                              sizes up to 8192, else two kernels with the tiles in
+ *                              fold_scratch (kib_grid_to_image_fold_bytes bytes);
  *   kib_grid_to_image_rows     one size-point inverse FFT per image row in shared memory
  *                              with the layer_to_image arithmetic (see kib_layer_to_image)
  *                              applied from registers; accumulates into image_plane.
@@ -185,6 +187,10 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
  * (callers then use kib_grid_to_layer + kib_fft_plan2d_exec + kib_layer_to_image). */
 int kib_grid_to_image_supported(int size, int grid_size, int dtype);
 int kib_grid_to_image_fold_bytes(int size, int grid_size, int64_t *bytes);
+/* Kernels one kib_grid_to_image_columns call launches: 1 where the column pass runs as a single
+ * thread-block-cluster kernel (fold butterflies exchanged through distributed shared memory,
+ * no fold tiles in global memory: sizes up to 8192), 2 (fold + tile transforms) otherwise. */
+int kib_grid_to_image_columns_kernels(int size);
 int kib_grid_to_image_columns(void *scratch, int scratch_row_stride, int size,
                               const void *grid_plane, int grid_row_stride, int grid_size,
                               void *fold_scratch, int dtype, kib_stream_t stream);

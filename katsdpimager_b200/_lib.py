@@ -71,6 +71,7 @@ SIGNATURES = {
     'kib_grid_to_image_supported': [_i, _i, _i],
     'kib_grid_to_image_columns': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_grid_to_image_fold_bytes': [_i, _i, POINTER(c_int64)],
+    'kib_grid_to_image_columns_kernels': [_i],
     'kib_image_to_grid_rows': [_vp, _i, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
     'kib_image_to_grid_columns': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
@@ -160,10 +161,12 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
     if name in _ONE_KERNEL:
         kernel_launches += 1
-    elif name in ('kib_grid_to_image_columns', 'kib_image_to_grid_columns'):
-        kernel_launches += 2                 # fold / unfold + column transforms
+    elif name == 'kib_grid_to_image_columns':
+        kernel_launches += load().kib_grid_to_image_columns_kernels(int(args[2]))
+    elif name == 'kib_image_to_grid_columns':
+        kernel_launches += 2                 # column transforms + unfold
     elif name == 'kib_grid_to_image':
-        kernel_launches += 3                 # fold + column transforms + row pass
+        kernel_launches += 1 + load().kib_grid_to_image_columns_kernels(int(args[8]))
     elif name == 'kib_clean_minor_cycles':
         kernel_launches += int(args[26])     # one launch per requested cycle
 

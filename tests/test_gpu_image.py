@@ -179,7 +179,8 @@ def test_grid_to_image_fused_vs_oracle(gpu, oracle, pixels, grid_size, pols):
         rms = np.sqrt(np.mean((actual - expected) ** 2)) / np.abs(expected).max()
         assert rms < 2e-6
         assert np.abs(actual - expected).max() / np.abs(expected).max() < 2e-5
-    assert _lib.kernel_launches - before == 2 * 3 * pols     # three kernels per plane
+    per_plane = 1 + _lib.load().kib_grid_to_image_columns_kernels(pixels)
+    assert _lib.kernel_launches - before == 2 * per_plane * pols
     # accumulates into the image
     g2i()
     np.testing.assert_allclose(g2i.buffer('image').get(queue), 2 * actual, rtol=1e-5, atol=1e-3)
