@@ -307,6 +307,11 @@ int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol
                            double loop_gain, double threshold, int max_cycles,
                            void *components, int component_stride, int32_t *state,
                            void *row_scratch, int dtype, kib_stream_t stream);
+/* Kernels one kib_clean_minor_cycles call launches (launch accounting): the row-maxima
+ * pass plus ONE cooperative persistent kernel that runs every cycle of the batch behind a grid
+ * barrier (float32), or -- float64, KIB_CLEAN_ROUTE=pdl, or no cooperative launch -- one
+ * kernel per cycle.  `state` must hold 16 int32 (zeroed by the caller before every call). */
+int kib_clean_minor_cycles_launches(int max_cycles, int dtype);
 
 /* kib_psf_patch replaces PsfPatch.__call__ (clean.py:123-163) + psf_patch.mako:
  * bound[0] = max |x - mid_x|, bound[1] = max |y - mid_y| over pixels in

@@ -90,6 +90,7 @@ SIGNATURES = {
                                _vp, _vp, _vp,
                                _d, _d, _i,
                                _vp, _i, _vp, _vp, _i, _vp],
+    'kib_clean_minor_cycles_launches': [_i, _i],
     'kib_psf_patch': [_vp, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _i, _vp],
     'kib_abs_histogram': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _vp, _i, _vp],
     'kib_rank': [_vp, _i, _i64, _i, _i, _i, _i, _d, _vp, _i, _vp],
@@ -168,7 +169,7 @@ def call(name, *args):
     elif name == 'kib_grid_to_image':
         kernel_launches += 1 + load().kib_grid_to_image_columns_kernels(int(args[8]))
     elif name == 'kib_clean_minor_cycles':
-        kernel_launches += int(args[26])     # one launch per requested cycle
+        kernel_launches += load().kib_clean_minor_cycles_launches(int(args[26]), int(args[31]))
 
 
 def grid_to_image_fold_bytes(size, grid_size):

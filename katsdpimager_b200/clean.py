@@ -490,10 +490,10 @@ class Clean(accel.OperationSequence):
         self._capacity = 0
         self._components = None
         self._components_host = None
-        self._state = accel.DeviceArray(command_queue.context, (4,), np.int32)
+        self._state = accel.DeviceArray(command_queue.context, (16,), np.int32)
         self._row_scratch = accel.DeviceArray(
             command_queue.context, (tile_shape[0] * (template.dtype.itemsize + 4),), np.uint8)
-        self._state_host = accel.HostArray((4,), np.int32, context=command_queue.context)
+        self._state_host = accel.HostArray((16,), np.int32, context=command_queue.context)
         self._pending = []
         self._pending_key = None
         self._cycles_since_reset = 0

@@ -17,6 +17,8 @@
 // peak, so no cycle ever waits for the host.
 #include "kib_common.cuh"
 #include <climits>
+#include <cstdlib>
+#include <cstring>
 
 namespace kib {
 
@@ -272,6 +274,166 @@ struct CleanStepParams {
 
 __device__ __forceinline__ int floordiv32(int a) { return a >> 5; }   // arithmetic shift = floor
 
+// Geometry of one minor cycle: the patch rectangle (clean.py:1024-1043) clipped to the image
+// and the lattice cells (32 x 32, aligned with the tiles, extended over the border) under it.
+struct CleanCycle {
+    int pos_x, pos_y;
+    int cx0, cy0, cx1, cy1;       // clipped patch
+    int psf_x0, psf_y0;           // psf x = image x + psf_x0
+    int cell_x0, cell_y0;         // first lattice cell
+    int cells_x, cells_y;
+};
+
+__device__ __forceinline__ CleanCycle clean_cycle_geometry(const CleanStepParams &prm,
+                                                           int pos_y, int pos_x)
+{
+    CleanCycle g;
+    g.pos_x = pos_x;
+    g.pos_y = pos_y;
+    const int px0 = pos_x - prm.patch_w / 2, py0 = pos_y - prm.patch_h / 2;
+    g.cx0 = max(px0, 0);
+    g.cy0 = max(py0, 0);
+    g.cx1 = min(px0 + prm.patch_w, prm.width);
+    g.cy1 = min(py0 + prm.patch_h, prm.height);
+    g.psf_x0 = prm.psf_width / 2 - prm.patch_w / 2 - px0;
+    g.psf_y0 = prm.psf_height / 2 - prm.patch_h / 2 - py0;
+    g.cell_x0 = floordiv32(g.cx0 - prm.border);
+    g.cell_y0 = floordiv32(g.cy0 - prm.border);
+    g.cells_x = floordiv32(g.cx1 - 1 - prm.border) - g.cell_x0 + 1;
+    g.cells_y = floordiv32(g.cy1 - 1 - prm.border) - g.cell_y0 + 1;
+    return g;
+}
+
+// Subtract the patch from the pixels of lattice cell (cell_x, cell_y) and recompute the peak
+// of its tile from the values still in registers.  One block of CLEAN_THREADS threads.
+template <typename Real, int P, int MODE>
+__device__ __forceinline__ void clean_cell(const CleanStepParams &prm, const CleanCycle &g,
+                                           const Real (&scale)[P], int cell_x, int cell_y,
+                                           Best<Real> *scratch)
+{
+    Real *const dirty = static_cast<Real *>(prm.dirty);
+    const Real *const psf = static_cast<const Real *>(prm.psf);
+    const int W = prm.width, H = prm.height, border = prm.border;
+    const int rx0 = border + cell_x * TILE, ry0 = border + cell_y * TILE;
+    const bool is_tile = cell_x >= 0 && cell_x < prm.tiles_x && cell_y >= 0 && cell_y < prm.tiles_y;
+    const bool touches = rx0 < g.cx1 && rx0 + TILE > g.cx0 && ry0 < g.cy1 && ry0 + TILE > g.cy0;
+    if (!touches) return;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = rx0 + lx;
+    Best<Real> best;
+    best.value = 0;
+    best.key = INT_MAX;
+    const bool x_in_patch = x >= g.cx0 && x < g.cx1;
+    const bool x_in_tile = is_tile && x >= border && x < W - border;
+#pragma unroll
+    for (int k = 0; k < TILE / 8; k++) {
+        const int y = ry0 + ly + 8 * k;
+        const bool in_patch = x_in_patch && y >= g.cy0 && y < g.cy1;
+        const bool in_tile = x_in_tile && y >= border && y < H - border;
+        if (in_patch || in_tile) {
+            const long long addr = (long long) y * prm.row_stride + x;
+            Real pix[P];
+            if (in_patch) {
+                const long long paddr = (long long) (y + g.psf_y0) * prm.psf_row_stride + x + g.psf_x0;
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    const Real d = dirty[p * prm.pol_stride + addr];
+                    const Real s = __ldg(psf + p * prm.psf_pol_stride + paddr);
+                    pix[p] = add_rn_(d, -mul_rn_(scale[p], s));
+                    dirty[p * prm.pol_stride + addr] = pix[p];
+                }
+            } else {
+                const int np = MODE == KIB_CLEAN_I ? 1 : P;
+#pragma unroll
+                for (int p = 0; p < P; p++)
+                    if (p < np) pix[p] = dirty[p * prm.pol_stride + addr];
+            }
+            if (in_tile) {
+                const Real value = clean_metric<Real, MODE>(pix, P);
+                if (value > best.value) {
+                    best.value = value;
+                    best.key = y * W + x;
+                }
+            }
+        }
+    }
+    if (is_tile) {
+        best = block_best(best, scratch);
+        if (threadIdx.x == 0) {
+            const long long idx = (long long) cell_y * prm.tile_stride + cell_x;
+            static_cast<Real *>(prm.tile_max)[idx] = best.value;
+            prm.tile_pos[idx] = best.key == INT_MAX ? make_int2(rx0, ry0)
+                                                    : make_int2(best.key / W, best.key % W);
+        }
+    }
+}
+
+// Model image and component list (clean.py:1047, :882; imaging.py:389-396); one thread.
+template <typename Real, int P>
+__device__ __forceinline__ void clean_record(const CleanStepParams &prm, const CleanCycle &g,
+                                             const Real (&scale)[P], Real peak_value, int done)
+{
+    Real *const model = static_cast<Real *>(prm.model);
+    char *rec = static_cast<char *>(prm.components) + (long long) done * prm.component_stride;
+    reinterpret_cast<int *>(rec)[0] = g.pos_y;
+    reinterpret_cast<int *>(rec)[1] = g.pos_x;
+    Real *vals = reinterpret_cast<Real *>(rec + 8);
+    vals[0] = peak_value;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const long long c = p * prm.pol_stride + (long long) g.pos_y * prm.row_stride + g.pos_x;
+        model[c] = add_rn_(model[c], scale[p]);
+        vals[1 + p] = scale[p];
+    }
+}
+
+// Refresh the row maxima of the tile rows a cycle touched (one warp per row), then take the
+// first maximum over rows -- the same answer as np.argmax over all tiles -- and publish the
+// next peak.  Whole block; all tile updates of the cycle must be visible.
+template <typename Real, int P>
+__device__ __forceinline__ void clean_next_peak(const CleanStepParams &prm, const CleanCycle &g,
+                                                Best<Real> *scratch)
+{
+    Real *const row_max = static_cast<Real *>(prm.row_max);
+    const Real *const tile_max = static_cast<const Real *>(prm.tile_max);
+    const Real *const dirty = static_cast<const Real *>(prm.dirty);
+    int ty0 = g.cell_y0, ty1 = g.cell_y0 + g.cells_y;
+    if (ty0 < 0) ty0 = 0;
+    if (ty1 > prm.tiles_y) ty1 = prm.tiles_y;
+    for (int ty = ty0 + (threadIdx.x >> 5); ty < ty1; ty += CLEAN_THREADS / 32)
+        tile_row_max(tile_max, prm.tile_stride, prm.tiles_x, ty, row_max, prm.row_arg);
+    __syncthreads();
+    Best<Real> best;
+    best.value = -1;
+    best.key = INT_MAX;
+    for (int ty = threadIdx.x; ty < prm.tiles_y; ty += CLEAN_THREADS) {
+        const Real value = row_max[ty];
+        if (value > best.value) {
+            best.value = value;
+            best.key = ty;
+        }
+    }
+    best = block_best(best, scratch);
+    if (threadIdx.x == 0) {
+        int2 pos = make_int2(0, 0);
+        Real value = 0;
+        if (best.key != INT_MAX) {
+            const int ty = best.key, tx = prm.row_arg[ty];
+            pos = __ldcg(prm.tile_pos + (long long) ty * prm.tile_stride + tx);
+            value = best.value;
+        }
+        static_cast<Real *>(prm.peak_value)[0] = value;
+        prm.peak_pos[0] = pos.x;
+        prm.peak_pos[1] = pos.y;
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            static_cast<Real *>(prm.peak_pixel)[p] =
+                __ldcg(dirty + p * prm.pol_stride + (long long) pos.x * prm.row_stride + pos.y);
+    }
+}
+
+// One launch per minor cycle, consecutive launches overlapped by programmatic dependent
+// launch.  Used when a cooperative launch is not possible (see clean_persistent_kernel).
 template <typename Real, int P, int MODE>
 __global__ void __launch_bounds__(CLEAN_THREADS)
 clean_step_kernel(const CleanStepParams prm)
@@ -288,101 +450,25 @@ clean_step_kernel(const CleanStepParams prm)
     // Uniform across the grid: state[1] is only ever written by launches in which every
     // block takes the "below threshold" exit.
     if (__ldcg(state + 1) != 0) return;
-    Real *const peak_value = static_cast<Real *>(prm.peak_value);
-    Real *const peak_pixel = static_cast<Real *>(prm.peak_pixel);
-    const Real pv = __ldcg(peak_value);
+    const Real pv = __ldcg(static_cast<Real *>(prm.peak_value));
     const int done = __ldcg(state);
     if ((double) pv < prm.threshold || done >= prm.max_components) {
         if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (double) pv < prm.threshold)
             state[1] = 1;
         return;
     }
-    const int pos_y = __ldcg(prm.peak_pos), pos_x = __ldcg(prm.peak_pos + 1);
+    const CleanCycle g = clean_cycle_geometry(prm, __ldcg(prm.peak_pos), __ldcg(prm.peak_pos + 1));
     Real scale[P];
 #pragma unroll
-    for (int p = 0; p < P; p++) scale[p] = mul_rn_((Real) prm.loop_gain, __ldcg(peak_pixel + p));
-
-    Real *const dirty = static_cast<Real *>(prm.dirty);
-    const Real *const psf = static_cast<const Real *>(prm.psf);
-    const int W = prm.width, H = prm.height, border = prm.border;
-    // Patch rectangle (clean.py:1024-1043), clipped to the image
-    const int px0 = pos_x - prm.patch_w / 2, py0 = pos_y - prm.patch_h / 2;
-    const int cx0 = max(px0, 0), cy0 = max(py0, 0);
-    const int cx1 = min(px0 + prm.patch_w, W), cy1 = min(py0 + prm.patch_h, H);
-    const int psf_x0 = prm.psf_width / 2 - prm.patch_w / 2 - px0;    // psf x = image x + psf_x0
-    const int psf_y0 = prm.psf_height / 2 - prm.patch_h / 2 - py0;
-    // This block's cell of the tile lattice (extended over the border region)
-    const int cell_x = floordiv32(cx0 - border) + blockIdx.x;
-    const int cell_y = floordiv32(cy0 - border) + blockIdx.y;
-    const int rx0 = border + cell_x * TILE, ry0 = border + cell_y * TILE;
-    const bool is_tile = cell_x >= 0 && cell_x < prm.tiles_x && cell_y >= 0 && cell_y < prm.tiles_y;
-    const bool touches = rx0 < cx1 && rx0 + TILE > cx0 && ry0 < cy1 && ry0 + TILE > cy0;
-
-    if (touches) {
-        const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-        const int x = rx0 + lx;
-        Best<Real> best;
-        best.value = 0;
-        best.key = INT_MAX;
-        const bool x_in_patch = x >= cx0 && x < cx1;
-        const bool x_in_tile = is_tile && x >= border && x < W - border;
-#pragma unroll
-        for (int k = 0; k < TILE / 8; k++) {
-            const int y = ry0 + ly + 8 * k;
-            const bool in_patch = x_in_patch && y >= cy0 && y < cy1;
-            const bool in_tile = x_in_tile && y >= border && y < H - border;
-            if (in_patch || in_tile) {
-                const long long addr = (long long) y * prm.row_stride + x;
-                Real pix[P];
-                if (in_patch) {
-                    const long long paddr = (long long) (y + psf_y0) * prm.psf_row_stride + x + psf_x0;
-#pragma unroll
-                    for (int p = 0; p < P; p++) {
-                        const Real d = dirty[p * prm.pol_stride + addr];
-                        const Real s = __ldg(psf + p * prm.psf_pol_stride + paddr);
-                        pix[p] = add_rn_(d, -mul_rn_(scale[p], s));
-                        dirty[p * prm.pol_stride + addr] = pix[p];
-                    }
-                } else {
-                    const int np = MODE == KIB_CLEAN_I ? 1 : P;
-#pragma unroll
-                    for (int p = 0; p < P; p++)
-                        if (p < np) pix[p] = dirty[p * prm.pol_stride + addr];
-                }
-                if (in_tile) {
-                    const Real value = clean_metric<Real, MODE>(pix, P);
-                    if (value > best.value) {
-                        best.value = value;
-                        best.key = y * W + x;
-                    }
-                }
-            }
-        }
-        if (is_tile) {
-            best = block_best(best, scratch);
-            if (threadIdx.x == 0) {
-                const long long idx = (long long) cell_y * prm.tile_stride + cell_x;
-                static_cast<Real *>(prm.tile_max)[idx] = best.value;
-                prm.tile_pos[idx] = best.key == INT_MAX ? make_int2(rx0, ry0)
-                                                        : make_int2(best.key / W, best.key % W);
-            }
-        }
-    }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        // model image and component list (clean.py:1047, :882; imaging.py:389-396)
-        Real *const model = static_cast<Real *>(prm.model);
-        char *rec = static_cast<char *>(prm.components) + (long long) done * prm.component_stride;
-        reinterpret_cast<int *>(rec)[0] = pos_y;
-        reinterpret_cast<int *>(rec)[1] = pos_x;
-        Real *vals = reinterpret_cast<Real *>(rec + 8);
-        vals[0] = pv;
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            const long long c = p * prm.pol_stride + (long long) pos_y * prm.row_stride + pos_x;
-            model[c] = add_rn_(model[c], scale[p]);
-            vals[1 + p] = scale[p];
-        }
-    }
+    for (int p = 0; p < P; p++)
+        scale[p] = mul_rn_((Real) prm.loop_gain, __ldcg(static_cast<Real *>(prm.peak_pixel) + p));
+    // the launch grid covers the largest number of cells a patch can touch; blocks beyond this
+    // cycle's cells have nothing to subtract
+    if ((int) blockIdx.x < g.cells_x && (int) blockIdx.y < g.cells_y)
+        clean_cell<Real, P, MODE>(prm, g, scale, g.cell_x0 + blockIdx.x, g.cell_y0 + blockIdx.y,
+                                  scratch);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        clean_record<Real, P>(prm, g, scale, pv, done);
     // Last block to finish selects the next peak.
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -393,47 +479,174 @@ clean_step_kernel(const CleanStepParams prm)
     __syncthreads();
     if (is_last) {
         __threadfence();
-        // Refresh the row maxima of the tile rows this cycle touched (one warp per row), then
-        // take the first maximum over rows: the same answer as np.argmax over all tiles.
+        clean_next_peak<Real, P>(prm, g, scratch);
+        if (threadIdx.x == 0) {
+            // The cycle count is published only here, after every block of this launch has
+            // taken its ticket: a block that starts late must still see `done`, not done + 1
+            // (it would skip its share of the subtraction on the last cycle of a batch).
+            state[0] = done + 1;
+            state[2] = 0;
+        }
+    }
+}
+
+// All cycles of a batch in ONE cooperative launch (single precision): the blocks stay
+// resident and share out the lattice cells of each cycle.  A cycle is one chain of dependent
+// round trips to L2, so the protocol is built to keep that chain short:
+//   * arrival = one acq_rel atomic per block; the last arrival selects the next peak from one
+//     parallel load of candidates (row maxima of untouched tile rows, tiles of touched rows);
+//   * the next peak travels to the other blocks as two self-validating 16-byte packets
+//     {cycle, y << 16 | x, value, pixel[0]}, {cycle, pixel[1..3]} that they poll with acquire
+//     loads -- no separate flag; polling is relaxed, with one acquire fence per cycle and block.
+// state: [0] cycles done, [1] stopped by threshold, [2] arrivals, [4..7] / [8..11] packets.
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_v4(uint4 *p, uint4 v)
+{
+    asm volatile("st.release.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int atom_add_release(int *p, int v)
+{
+    int old;
+    asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(CLEAN_THREADS)
+clean_persistent_kernel(const CleanStepParams prm)
+{
+    typedef float Real;
+    __shared__ Best<Real> scratch[33];
+    __shared__ int is_last;
+    __shared__ unsigned s_peak[8];                       // y, x, value, pixel[0..3]
+    int *state = prm.state;
+    uint4 *const packets = reinterpret_cast<uint4 *>(state + 4);
+    const int nblocks = (int) gridDim.x;
+    const Real *const dirty = static_cast<const Real *>(prm.dirty);
+    for (int done = 0; done < prm.max_components; done++) {
+        // ---- this cycle's peak
+        if (threadIdx.x == 0) {
+            if (done == 0) {
+                s_peak[0] = (unsigned) __ldcg(prm.peak_pos);
+                s_peak[1] = (unsigned) __ldcg(prm.peak_pos + 1);
+                s_peak[2] = __float_as_uint(__ldcg(static_cast<const Real *>(prm.peak_value)));
+                for (int p = 0; p < P; p++)
+                    s_peak[3 + p] = __float_as_uint(__ldcg(static_cast<const Real *>(prm.peak_pixel) + p));
+            } else {
+                uint4 a, b;
+                // relaxed polling (an acquire load would invalidate this SM's L1 on every
+                // iteration), one acquire fence once the packets of this cycle are in
+                do {
+                    a = ld_relaxed_v4(packets);
+                    b = P > 1 ? ld_relaxed_v4(packets + 1) : a;
+                } while (a.x != (unsigned) done || b.x != (unsigned) done);
+                __threadfence();
+                s_peak[0] = a.y >> 16;
+                s_peak[1] = a.y & 0xffffu;
+                s_peak[2] = a.z;
+                s_peak[3] = a.w;
+                s_peak[4] = b.y;
+                s_peak[5] = b.z;
+                s_peak[6] = b.w;
+            }
+        }
+        __syncthreads();
+        const Real pv = __uint_as_float(s_peak[2]);
+        if ((double) pv < prm.threshold) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) state[1] = 1;
+            break;                                       // uniform: every block saw the same peak
+        }
+        const CleanCycle g = clean_cycle_geometry(prm, (int) s_peak[0], (int) s_peak[1]);
+        Real scale[P];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            scale[p] = mul_rn_((Real) prm.loop_gain, __uint_as_float(s_peak[3 + p]));
+        const int cells = g.cells_x * g.cells_y;
+        for (int cell = blockIdx.x; cell < cells; cell += nblocks) {
+            const int cy = cell / g.cells_x, cx = cell - cy * g.cells_x;
+            clean_cell<Real, P, MODE>(prm, g, scale, g.cell_x0 + cx, g.cell_y0 + cy, scratch);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) clean_record<Real, P>(prm, g, scale, pv, done);
+        // ---- arrive; the last arrival finds the next peak and publishes it
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            is_last = atom_add_release(state + 2, 1) == nblocks - 1;
+            if (is_last) __threadfence();
+        }
+        __syncthreads();
+        if (!is_last) continue;
+
         Real *const row_max = static_cast<Real *>(prm.row_max);
         const Real *const tile_max = static_cast<const Real *>(prm.tile_max);
-        int ty0 = floordiv32(cy0 - border), ty1 = floordiv32(cy1 - 1 - border) + 1;
+        int ty0 = g.cell_y0, ty1 = g.cell_y0 + g.cells_y;
         if (ty0 < 0) ty0 = 0;
         if (ty1 > prm.tiles_y) ty1 = prm.tiles_y;
-        for (int ty = ty0 + (threadIdx.x >> 5); ty < ty1; ty += CLEAN_THREADS / 32)
-            tile_row_max(tile_max, prm.tile_stride, prm.tiles_x, ty, row_max, prm.row_arg);
-        __syncthreads();
         Best<Real> best;
         best.value = -1;
         best.key = INT_MAX;
-        for (int ty = threadIdx.x; ty < prm.tiles_y; ty += CLEAN_THREADS) {
-            const Real value = row_max[ty];
-            if (value > best.value) {
-                best.value = value;
-                best.key = ty;
+        // tile rows this cycle did not touch: their stored maxima
+        for (int ty = threadIdx.x; ty < prm.tiles_y; ty += CLEAN_THREADS)
+            if (ty < ty0 || ty >= ty1) {
+                Best<Real> c;
+                c.value = __ldcg(row_max + ty);
+                c.key = ty * prm.tiles_x + __ldcg(prm.row_arg + ty);
+                best = better(best, c);
             }
+        // touched rows: one warp per row rescans the row and refreshes its stored maximum
+        const int lane = threadIdx.x & 31;
+        for (int ty = ty0 + (threadIdx.x >> 5); ty < ty1; ty += CLEAN_THREADS / 32) {
+            Best<Real> row;
+            row.value = -1;
+            row.key = INT_MAX;
+            for (int tx = lane; tx < prm.tiles_x; tx += 32) {
+                const Real value = __ldcg(tile_max + (long long) ty * prm.tile_stride + tx);
+                if (value > row.value) {
+                    row.value = value;
+                    row.key = tx;
+                }
+            }
+            row = warp_best(row);
+            if (lane == 0) {
+                row_max[ty] = row.value;
+                prm.row_arg[ty] = row.key;
+            }
+            row.key += ty * prm.tiles_x;
+            best = better(best, row);
         }
         best = block_best(best, scratch);
         if (threadIdx.x == 0) {
             int2 pos = make_int2(0, 0);
             Real value = 0;
             if (best.key != INT_MAX) {
-                const int ty = best.key, tx = prm.row_arg[ty];
+                const int ty = best.key / prm.tiles_x, tx = best.key - ty * prm.tiles_x;
                 pos = __ldcg(prm.tile_pos + (long long) ty * prm.tile_stride + tx);
                 value = best.value;
             }
-            peak_value[0] = value;
+            Real pix[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                pix[p] = __ldcg(dirty + p * prm.pol_stride + (long long) pos.x * prm.row_stride + pos.y);
+            state[0] = done + 1;
+            state[2] = 0;
+            const unsigned seq = (unsigned) (done + 1);
+            if (P > 1)
+                st_release_v4(packets + 1, make_uint4(seq, __float_as_uint(pix[1]),
+                                                      __float_as_uint(pix[2]), __float_as_uint(pix[3])));
+            st_release_v4(packets, make_uint4(seq, ((unsigned) pos.x << 16) | (unsigned) pos.y,
+                                              __float_as_uint(value), __float_as_uint(pix[0])));
+            // the reference's slots (off the critical path)
+            static_cast<Real *>(prm.peak_value)[0] = value;
             prm.peak_pos[0] = pos.x;
             prm.peak_pos[1] = pos.y;
 #pragma unroll
-            for (int p = 0; p < P; p++)
-                peak_pixel[p] = __ldcg(dirty + p * prm.pol_stride
-                                       + (long long) pos.x * prm.row_stride + pos.y);
-            // The cycle count is published only here, after every block of this launch has
-            // taken its ticket: a block that starts late must still see `done`, not done + 1
-            // (it would skip its share of the subtraction on the last cycle of a batch).
-            state[0] = done + 1;
-            state[2] = 0;
+            for (int p = 0; p < P; p++) static_cast<Real *>(prm.peak_pixel)[p] = pix[p];
         }
     }
 }
@@ -536,6 +749,53 @@ static void launch_step_mode(const CleanStepParams &prm, int mode, dim3 grid, cu
         cudaLaunchKernelEx(&config, clean_step_kernel<Real, P, KIB_CLEAN_I>, prm);
     else
         cudaLaunchKernelEx(&config, clean_step_kernel<Real, P, KIB_CLEAN_SUMSQ>, prm);
+}
+
+// KIB_CLEAN_ROUTE=pdl forces one launch per cycle
+static bool clean_route_pdl()
+{
+    const char *route = getenv("KIB_CLEAN_ROUTE");
+    return route && strcmp(route, "pdl") == 0;
+}
+
+// Cooperative launch of clean_persistent_kernel with at most `cells` blocks (one lattice cell
+// per block and cycle when they all fit).  Returns 1 if the device cannot co-schedule it.
+template <int P, int MODE>
+static int launch_persistent_mode(const CleanStepParams &prm, int cells, cudaStream_t stream)
+{
+    auto kernel = clean_persistent_kernel<P, MODE>;
+    static int max_blocks = -1;                          // per instantiation
+    if (max_blocks < 0) {
+        int device = 0, cooperative = 0, per_sm = 0;
+        KIB_CUDA(cudaGetDevice(&device));
+        KIB_CUDA(cudaDeviceGetAttribute(&cooperative, cudaDevAttrCooperativeLaunch, device));
+        KIB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CLEAN_THREADS, 0));
+        max_blocks = cooperative ? per_sm * sm_count() : 0;
+    }
+    if (max_blocks < 1) return 1;
+    int blocks = cells < max_blocks ? cells : max_blocks;
+    void *args[] = {const_cast<CleanStepParams *>(&prm)};
+    KIB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kernel), dim3(blocks),
+                                         dim3(CLEAN_THREADS), args, 0, stream));
+    return 0;
+}
+
+static int launch_persistent(const CleanStepParams &prm, int P, int mode, int cells,
+                             cudaStream_t stream)
+{
+#define KIB_PERSISTENT(PP)                                                                      \
+    return mode == KIB_CLEAN_I ? launch_persistent_mode<PP, KIB_CLEAN_I>(prm, cells, stream)    \
+                               : launch_persistent_mode<PP, KIB_CLEAN_SUMSQ>(prm, cells, stream)
+    switch (P) {
+    case 1: KIB_PERSISTENT(1);
+    case 2: KIB_PERSISTENT(2);
+    case 3: KIB_PERSISTENT(3);
+    case 4: KIB_PERSISTENT(4);
+    default:
+        set_error("kib_clean_minor_cycles: num_pols must be 1..4, not %d", P);
+        return -1;
+    }
+#undef KIB_PERSISTENT
 }
 
 template <typename Real>
@@ -716,6 +976,11 @@ int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol
                 static_cast<const double *>(tile_max), tile_stride, tiles_x, tiles_y,
                 static_cast<double *>(prm.row_max), prm.row_arg);
     }
+    if (dtype == KIB_F32 && width <= 65536 && height <= 65536 && !clean_route_pdl()) {
+        const int rc = launch_persistent(prm, num_pols, mode, (int) (g.x * g.y), s);
+        if (rc <= 0) return rc;
+        // rc == 1: no cooperative launch on this device
+    }
     for (int i = 0; i < max_cycles; i++) {
         int rc = dtype == KIB_F32 ? launch_step<float>(prm, num_pols, mode, g, s)
                                   : launch_step<double>(prm, num_pols, mode, g, s);
@@ -723,6 +988,12 @@ int kib_clean_minor_cycles(void *dirty, void *model, int row_stride, int64_t pol
     }
     KIB_CHECK_LAUNCH();
     return 0;
+}
+
+int kib_clean_minor_cycles_launches(int max_cycles, int dtype)
+{
+    // row maxima + cycles
+    return 1 + ((clean_route_pdl() || dtype != KIB_F32) ? max_cycles : 1);
 }
 
 int kib_psf_patch(const void *psf, int row_stride, int64_t pol_stride, int num_pols,
