@@ -3,28 +3,32 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--dumps T]
 
-One *step* = one dirty-image pass over one synthetic MeerKAT channel at BASELINE
-config 2 (8192^2 image, 4 polarizations, 16 W slices, 7x7 support x 8 oversample):
-for every W slice { clear grid, grid the slice's visibilities, grid -> image for the 4
-polarizations (fused pruned transform: column pass + row pass with the taper / W-term
-epilogue) }.  With N > 1 every rank images its own channel on its own GPU (weak scaling, no
-collective on the data path).
+One *step* = one synthetic MeerKAT channel at BASELINE config 2 (8192^2 image, 4
+polarizations, 16 W slices, 7x7 support x 8 oversample, 7.26 M visibilities) IMAGED, i.e. the
+reference's ``frontend.process_channel`` (frontend.py:465-641) replayed by
+katsdpimager_b200/pipeline.py: robust weights -> PSF pass -> MAJOR major cycles, each a dirty
+/ residual pass (W-stacked gridding + fused grid->image transform; from the second cycle on
+with image->grid + degridding of the model), a noise estimate and up to MINOR Hogbom minor
+cycles -> model added back -> final image.  With N > 1 every rank images its own channel on
+its own GPU (weak scaling; no collective on the data path) and stores its plane in a shared
+FITS cube.
 
-`value`  = visibilities gridded per second over the whole step with inputs resident in HBM.
-`e2e`    = the same metric through the Imaging facade with HOST buffers: per 1 Mi-visibility
-           chunk set_coordinates/set_vis (H2D of pinned records) + grid, and a D2H read of
-           the dirty image, all inside the timed region; a few imagers on their own command
-           queues take channels in turn so that copies overlap kernels (ImagingPipeline).
+`value`  = visibilities gridded per second over the whole step (all passes) with the
+           visibility records already resident in HBM.
+`e2e`    = the same through the public API from HOST memory: per step the channel's pinned
+           records are uploaded once (H2D), the channel is imaged, and the final image is
+           written in FITS order into the mapped cube file (D2H), all inside the timed region.
 `roofline` = the kernel that takes most of the step (row pass of the fused transform, HBM
-           roofline over its algorithmic bytes); `roofline_columns`, `roofline_gridder` follow.
-`--impl reference` times the CPU oracle (port of the reference's --host path) on a bounded
-sample of the same workload with all host threads.
+           roofline over its algorithmic bytes); `rooflines` lists the other kernels of the path.
+`--impl reference` / `cpu_baseline` time the CPU oracle (port of the reference's --host
+path) on all host threads on a bounded sample: the same fraction of every stage of the step.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
@@ -46,9 +50,16 @@ KERNEL_WIDTH = 7
 OVERSAMPLE = 8
 NUM_CHANNELS = 64
 VIS_BLOCK = 1 << 20
-E2E_DEPTH = int(os.environ.get('KIB_E2E_DEPTH', '3'))   # imagers (command queues) in flight in the e2e leg
+MAJOR = 3
+MINOR = 1000
+ROBUSTNESS = 0.0
 METRIC = 'gridded_visibilities_per_sec'
 UNIT = 'vis/s'
+#: CLEAN work of the step as the B200 run of this synthetic channel executes it (CLEAN is bit
+#: exact, so the host path would run the same cycles): PSF patch side and minor cycles over the
+#: MAJOR major cycles.  Only used to size the CPU sample; the GPU arm reports what it ran.
+NOMINAL_PATCH = 1501
+NOMINAL_MINOR = 300
 
 
 def make_parameters(channel):
@@ -59,9 +70,18 @@ def make_parameters(channel):
     fixed = prm.FixedImageParameters([1, 2, 3, 4], np.float32)
     ip = prm.ImageParameters(fixed, wavelength=wavelength, pixels=PIXELS, array=array,
                              image_oversample=5.0)
-    fixed_grid = prm.FixedGridParameters(7.0, OVERSAMPLE, 4, array.longest_baseline, KERNEL_WIDTH)
+    fixed_grid = prm.FixedGridParameters(7.0, OVERSAMPLE, 4, array.longest_baseline, KERNEL_WIDTH,
+                                         degrid=True)
     gp = prm.GridParameters(fixed_grid, W_SLICES, W_PLANES)
     return array, ip, gp
+
+
+def clean_parameters():
+    """The reference's defaults (frontend.py:337-351) with --major 3 --minor 1000."""
+    from katsdpimager_b200 import clean
+    return prm.CleanParameters(minor=MINOR, loop_gain=0.1, major_gain=0.85, threshold=5.0,
+                               mode=clean.CLEAN_SUMSQ, psf_cutoff=0.01, psf_limit=0.5,
+                               border=0.02)
 
 
 def make_channel(channel, dumps, seed=1):
@@ -81,8 +101,22 @@ def make_channel(channel, dumps, seed=1):
 
 
 def flops_per_vis(kernel_width, pols):
-    """Algorithmic work of gridding one visibility: K^2 (8 P + 6)."""
+    """Algorithmic work of (de)gridding one visibility: K^2 (8 P + 6)."""
     return kernel_width ** 2 * (8 * pols + 6)
+
+
+def step_work(slices):
+    """Units of work in one step, shared by both arms."""
+    total_vis = sum(len(s) for s in slices)
+    planes = POLS * sum(1 for s in slices if len(s))
+    return {
+        'vis': total_vis,
+        'gridded_vis': (1 + MAJOR) * total_vis,               # PSF pass + one pass per major cycle
+        'degridded_vis': (MAJOR - 1) * total_vis,
+        'weighted_vis': total_vis,
+        'grid_to_image_planes': (1 + MAJOR) * planes,
+        'image_to_grid_planes': (MAJOR - 1) * planes,
+    }
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -198,92 +232,150 @@ class Ranks:
 
 
 # --------------------------------------------------------------------------- CPU baseline
-def cpu_sample(ip, gp, slices, threads, vis_per_thread, fft_planes):
-    """Time the CPU oracle on a bounded sample: `threads` independent chunks of
-    `vis_per_thread` visibilities gridded concurrently (one grid per thread, as separate
-    channels would be), and `fft_planes` (W slice, polarization) planes through
-    ifft2 + epilogue concurrently.  Returns per-visibility and per-plane wall times."""
-    import oracle
-    oracle.host.build()
-    lut = oracle.convolution_kernel(ip, gp)
-    max_uv = int(simulate.longest_baseline() / ip.cell_size)
-    size = 2 * (max_uv + KERNEL_WIDTH // 2 + 1)
-    records = np.concatenate([s for s in slices if len(s)]).view(np.recarray)
-    records = records[:threads * vis_per_thread]
-    chunks = np.array_split(np.arange(len(records)), threads)
-    wgrid = np.ones((POLS, size, size), np.float32)
+class CpuSample:
+    """A bounded sample of one step for the CPU oracle: the SAME fraction `phi` of every stage
+    of the step (gridding, degridding, both transforms, CLEAN), each stage spread over all
+    host threads the way independent channels would be.  One call of :meth:`run` is one
+    reference-arm step; its wall time / phi estimates the channel time."""
 
-    def grid_chunk(idx):
-        r = records[idx]
-        values = np.zeros((POLS, size, size), np.complex64)
-        oracle.grid(lut, values, wgrid, r.uv, r.sub_uv, r.w_plane, r.vis)
-        return values
+    def __init__(self, ip, gp, slices, threads, phi):
+        import oracle
+        oracle.host.build()
+        self.oracle = oracle
+        self.ip, self.gp = ip, gp
+        self.threads = threads
+        self.phi = phi
+        work = step_work(slices)
+        self.work = work
+        records = np.concatenate([s for s in slices if len(s)]).view(np.recarray)
+        self.n_grid = max(threads, int(round(phi * work['gridded_vis'])))
+        self.n_degrid = max(threads, int(round(phi * work['degridded_vis'])))
+        self.n_g2i = max(1, int(round(phi * work['grid_to_image_planes'])))
+        self.n_i2g = max(1, int(round(phi * work['image_to_grid_planes'])))
+        self.n_clean = max(1, int(round(phi * NOMINAL_MINOR)))
+        self.records = records[:max(self.n_grid, self.n_degrid)]
+        self.lut = oracle.convolution_kernel(ip, gp)
+        max_uv = int(simulate.longest_baseline() / ip.cell_size)
+        self.size = 2 * (max_uv + KERNEL_WIDTH // 2 + 1)
+        self.taper = oracle.taper(gp, ip.pixels, np.float32)
+        self.lm_scale = float(ip.pixel_size)
+        self.lm_bias = -0.5 * ip.pixels * self.lm_scale
+        self.mid_w = prm.slice_mid_w(ip, gp)
+        self.pool = ThreadPoolExecutor(threads)
+        rs = np.random.RandomState(4)
+        size = self.size
+        self.wgrid = np.ones((POLS, size, size), np.float32)
+        self.model_grid = (rs.standard_normal((POLS, size, size))
+                           + 1j * rs.standard_normal((POLS, size, size))).astype(np.complex64)
+        # CLEAN inputs: noise + a few sources, Gaussian PSF with a pedestal
+        n = ip.pixels
+        g = np.exp(-0.5 * ((np.arange(n) - n // 2) / 3.0) ** 2).astype(np.float32)
+        p = np.exp(-0.5 * ((np.arange(n) - n // 2) / (n / 16.0)) ** 2).astype(np.float32)
+        psf1 = np.outer(g, g) + np.float32(0.05) * np.outer(p, p)
+        self.psf = np.ascontiguousarray(np.broadcast_to(psf1, (POLS, n, n)))
+        self.dirty = (0.01 * rs.standard_normal((POLS, n, n))).astype(np.float32)
+        for _ in range(30):
+            y, x = rs.randint(n // 8, n - n // 8, 2)
+            self.dirty[:, y, x] += rs.uniform(1, 5)
+        self.model = np.zeros_like(self.dirty)
+        self.description = (
+            'oracle (C/numpy port of the reference --host path), {} threads, fraction {:.4g} of '
+            'every stage of one channel: {} vis gridded + {} degridded (chunks over threads), '
+            '{} grid->image + {} image->grid 8192^2 planes (row blocks over threads), {} CLEAN '
+            'cycles with a {}^2 x {} patch (1 thread, sequential by nature)'.format(
+                threads, phi, self.n_grid, self.n_degrid, self.n_g2i, self.n_i2g, self.n_clean,
+                NOMINAL_PATCH, POLS))
 
-    with ThreadPoolExecutor(threads) as pool:
-        list(pool.map(grid_chunk, [c[:1000] for c in chunks]))      # warm-up (page faults)
+    def _grid(self, n):
+        oracle, r = self.oracle, self.records[:n]
+        chunks = np.array_split(np.arange(n), self.threads)
+
+        def work(idx):
+            values = np.zeros((POLS, self.size, self.size), np.complex64)
+            c = r[idx]
+            oracle.grid(self.lut, values, self.wgrid, c.uv, c.sub_uv, c.w_plane, c.vis)
+            return values
+        return list(self.pool.map(work, chunks))
+
+    def _degrid(self, n):
+        oracle, r = self.oracle, self.records[:n]
+        chunks = np.array_split(np.arange(n), self.threads)
+
+        def work(idx):
+            c = r[idx]
+            vis = np.ascontiguousarray(c.vis)
+            oracle.degrid(self.lut, self.model_grid, c.uv, c.sub_uv, c.w_plane, c.weights, vis)
+            return float(vis[0, 0].real) if len(vis) else 0.0
+        return list(self.pool.map(work, chunks))
+
+    def run(self):
+        """One step; returns the wall time of each stage."""
+        oracle = self.oracle
+        times = {}
         t0 = time.monotonic()
-        grids = list(pool.map(grid_chunk, chunks))
-        t_grid = time.monotonic() - t0
-    taper = oracle.taper(gp, ip.pixels, np.float32)
-    lm_scale = float(ip.pixel_size)
-    lm_bias = -0.5 * ip.pixels * lm_scale
-    mid_w = prm.slice_mid_w(ip, gp)
-
-    def image_plane(k):
-        image = np.zeros((1, ip.pixels, ip.pixels), np.float32)
-        oracle.grid_to_image(grids[k % len(grids)][k % POLS:k % POLS + 1], image, taper,
-                             lm_scale, lm_bias, mid_w[k % W_SLICES])
-        return float(image[0, ip.pixels // 2, ip.pixels // 2])
-
-    fft_threads = min(threads, fft_planes)
-    with ThreadPoolExecutor(fft_threads) as pool:
+        grids = self._grid(self.n_grid)
+        times['grid'] = time.monotonic() - t0
         t0 = time.monotonic()
-        list(pool.map(image_plane, range(fft_planes)))
-        t_fft = time.monotonic() - t0
-    return t_grid / len(records), t_fft / fft_planes, len(records), fft_threads
+        self._degrid(self.n_degrid)
+        times['degrid'] = time.monotonic() - t0
+        t0 = time.monotonic()
+        image = np.zeros((self.ip.pixels, self.ip.pixels), np.float32)
+        for k in range(self.n_g2i):
+            oracle.host.grid_to_image_threaded(
+                grids[k % len(grids)][k % POLS], image, self.taper, self.lm_scale, self.lm_bias,
+                np.float64(self.mid_w[k % W_SLICES]), self.pool, self.threads)
+        times['grid_to_image'] = time.monotonic() - t0
+        t0 = time.monotonic()
+        # image -> grid costs the same two 1-D passes and one elementwise pass per plane
+        for k in range(self.n_i2g):
+            oracle.host.grid_to_image_threaded(
+                grids[k % len(grids)][k % POLS], image, self.taper, self.lm_scale, self.lm_bias,
+                np.float64(-self.mid_w[k % W_SLICES]), self.pool, self.threads)
+        times['image_to_grid'] = time.monotonic() - t0
+        t0 = time.monotonic()
+        cp = clean_parameters()
+        host = oracle.CleanHost(self.ip.pixels, cp.border, cp.mode, cp.loop_gain, self.dirty,
+                                self.psf, self.model)
+        host.reset()
+        for _ in range(self.n_clean):
+            host((POLS, NOMINAL_PATCH, NOMINAL_PATCH), 0.0)
+        times['clean'] = time.monotonic() - t0
+        times['total'] = sum(times.values())
+        return times
 
-
-def cpu_channel_rate(ip, gp, slices, threads, vis_per_thread, fft_planes):
-    total_vis = sum(len(s) for s in slices)
-    planes = POLS * sum(1 for s in slices if len(s))
-    per_vis, per_plane, sample_vis, fft_threads = cpu_sample(
-        ip, gp, slices, threads, vis_per_thread, fft_planes)
-    seconds = per_vis * total_vis + per_plane * planes
-    sample = ('oracle (C/numpy port of the --host path): {} vis gridded on {} threads '
-              '({:.3g} us/vis wall) + {} of {} (w-slice, pol) planes through ifft2+epilogue on '
-              '{} threads ({:.3g} s/plane wall); channel time extrapolated linearly').format(
-        sample_vis, threads, per_vis * 1e6, fft_planes, planes, fft_threads, per_plane)
-    return total_vis / seconds, seconds, sample, {
-        'grid_vis_per_s': 1.0 / per_vis, 'image_planes_per_s': 1.0 / per_plane}
+    def close(self):
+        self.pool.shutdown()
 
 
 def run_reference(args, ranks):
     """--impl reference: the reference's CPU (--host) algorithm, as restated in oracle/,
-    with all host threads, on a bounded sample per step."""
+    with all host threads.  Every step really executes a bounded sample (fraction phi of a
+    channel); `ms_per_step` is its measured wall time and `value` the rate it implies."""
     if ranks.rank != 0:
         return
     threads = os.cpu_count() or 1
     array, ip, gp, slices = make_channel(0, args.dumps)
-    total_vis = sum(len(s) for s in slices)
-    rates, times = [], []
-    sample = ''
+    sample = CpuSample(ip, gp, slices, threads, args.cpu_fraction)
+    times = []
     for step in range(args.warmup + args.steps):
-        small = step < args.warmup
-        rate, seconds, sample, extra = cpu_channel_rate(
-            ip, gp, slices, threads, 2000 if small else args.cpu_vis, 1 if small else
-            max(1, min(threads, args.cpu_planes)))
-        if not small:
-            rates.append(rate)
-            times.append(seconds)
-    value = float(np.mean(rates))
+        t = sample.run()
+        if step >= args.warmup:
+            times.append(t)
+    sample.close()
+    seconds = float(np.mean([t['total'] for t in times]))
+    value = args.cpu_fraction * sample.work['gridded_vis'] / seconds
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': float(np.mean(times)) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': seconds * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(total_vis, args, 1),
+        'config': workload_config(sample.work['vis'], args, 1),
+        'step_is': 'fraction {:.4g} of one channel (see cpu_baseline.sample)'.format(
+            args.cpu_fraction),
+        'channels_imaged_per_sec': args.cpu_fraction / seconds,
+        'stage_seconds_per_step': {k: float(np.mean([t[k] for t in times])) for k in times[0]},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                         'sample': sample},
+                         'sample': sample.description},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -292,88 +384,85 @@ def run_reference(args, ranks):
 def workload_config(total_vis, args, world):
     return {
         'workload': ('BASELINE configs[1]: MeerKAT-64 L-band 4-pol, 8192^2 image, 16 w-slices, '
-                     '7x7 support x8 oversample; one channel per GPU per step (dirty image: '
-                     'grid all slices + fused pruned grid->image transform per plane)'),
+                     '7x7 support x8 oversample; one channel imaged per GPU per step '
+                     '(frontend.process_channel replay: robust weights, PSF, {} major cycles with '
+                     'degridding and up to {} minor cycles each, final image)'.format(MAJOR, MINOR)),
         'pixels': PIXELS, 'polarizations': POLS, 'w_slices': W_SLICES, 'w_planes': W_PLANES,
-        'kernel_width': KERNEL_WIDTH, 'oversample': OVERSAMPLE,
+        'kernel_width': KERNEL_WIDTH, 'oversample': OVERSAMPLE, 'major': MAJOR, 'minor': MINOR,
+        'weighting': 'robust {}'.format(ROBUSTNESS), 'degrid': True,
         'vis_per_channel': int(total_vis), 'dumps': args.dumps, 'channels_per_step': world,
         'parallelism': 'channel-parallel x{}'.format(world),
-        'l2': 'working set per step (grid 0.78 GB, layer 0.54 GB, image 1.07 GB, vis) exceeds '
+        'l2': 'working set per step (grids 1.6 GB, images 3.2 GB, records 0.4 GB) exceeds '
               'the 126 MB L2, no explicit flush',
     }
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def oracle_plane_check(imager, ip, gp, slices, mid_w, queue):
+    """Parity at the benchmark's own size: the sparsest non-empty W slice gridded and
+    transformed on the GPU against the CPU oracle (polarization 0 of the 8192^2 plane).
+    Returns RMS and maximum difference relative to the peak."""
+    import oracle
+    oracle.host.build()
+    sizes = [(len(s), i) for i, s in enumerate(slices) if len(s)]
+    n, w_slice = min(sizes)
+    records = slices[w_slice]
+    vis = _resident(queue, [records if i == w_slice else records[:0] for i in range(len(slices))])
+    imager.clear_dirty()
+    imager.clear_grid()
+    imager.set_resident(vis, w_slice, 0, n, 'vis')
+    imager.grid()
+    imager.grid_to_image(mid_w[w_slice])
+    actual = imager.get_buffer('dirty')[0]
+    wgrid = imager.get_buffer('weights_grid')
+    size = wgrid.shape[-1]
+    grid = np.zeros((POLS, size, size), np.complex64)
+    oracle.grid(oracle.convolution_kernel(ip, gp), grid, np.ascontiguousarray(wgrid),
+                np.ascontiguousarray(records.uv), np.ascontiguousarray(records.sub_uv),
+                np.ascontiguousarray(records.w_plane), np.ascontiguousarray(records.vis))
+    expected = np.zeros((1, ip.pixels, ip.pixels), np.float32)
+    oracle.grid_to_image(grid[:1], expected, oracle.taper(gp, ip.pixels, np.float32),
+                         float(ip.pixel_size), -0.5 * ip.pixels * float(ip.pixel_size),
+                         np.float64(mid_w[w_slice]))
+    peak = float(np.abs(expected).max())
+    diff = actual - expected[0]
+    return {'w_slice': int(w_slice), 'vis': int(n),
+            'rms_rel_peak': float(np.sqrt(np.mean(diff.astype(np.float64) ** 2)) / peak),
+            'max_rel_peak': float(np.abs(diff).max() / peak), 'bar': 1e-4}
+
+
+def _resident(queue, slices):
+    from katsdpimager_b200 import pipeline
+    return pipeline.ResidentVisibilities(queue, slices, POLS)
+
+
 def run_gpu(args, ranks):
-    from katsdpimager_b200 import _lib, accel, imaging, profiling, weight, clean
+    from katsdpimager_b200 import _lib, accel, imaging, io, pipeline, profiling, weight
 
     context = accel.Context(ranks.local_rank)
     queue = context.create_command_queue()
     channel = ranks.rank * (NUM_CHANNELS // max(ranks.world, 1)) % NUM_CHANNELS
     array, ip, gp, slices = make_channel(channel, args.dumps)
-    total_vis = sum(len(s) for s in slices)
-    max_slice = max(len(s) for s in slices)
-    max_vis = max(VIS_BLOCK, max_slice)
+    work = step_work(slices)
+    total_vis = work['vis']
     mid_w = prm.slice_mid_w(ip, gp)
-    cp = prm.CleanParameters(minor=1000, loop_gain=0.1, major_gain=0.85, threshold=5.0,
-                             mode=clean.CLEAN_SUMSQ, psf_cutoff=0.01, psf_limit=0.5, border=0.02)
-    wp = prm.WeightParameters(weight.WeightType.NATURAL)
+    cp = clean_parameters()
+    wp = prm.WeightParameters(weight.WeightType.ROBUST, ROBUSTNESS)
     template = imaging.ImagingTemplate(context, array, ip.fixed, wp, gp.fixed, cp)
-    imager = template.instantiate(queue, ip, gp, max_vis, 0, 1)
+    imager = template.instantiate(queue, ip, gp, VIS_BLOCK, 0, MAJOR)
     imager.ensure_all_bound()
-    imager.clear_weights()
-    imager.finalize_weights()          # natural weights: fill with ones
 
-    # ---- device-resident inputs: one (uv, w_plane, vis) buffer set per W slice
-    resident = []
-    for s in slices:
-        n = len(s)
-        if n == 0:
-            resident.append(None)
-            continue
-        bufs = {}
-        for name, data in (('uv', imaging._uv_view(s)), ('w_plane', s.w_plane), ('vis', s.vis)):
-            slot = imager.slots[name]
-            dev = accel.DeviceArray(context, slot.shape, slot.dtype, slot.required_padded_shape())
-            dev.set_region(queue, np.ascontiguousarray(data), np.s_[:n], np.s_[:n])
-            bufs[name] = dev
-        resident.append((n, bufs))
-    staging = {name: imager.buffer(name) for name in ('uv', 'w_plane', 'vis')}
     # e2e inputs live in pinned host memory (contract: H2D from pinned memory in the timed region)
     pinned_slices = []
     for s in slices:
         host = accel.HostArray((len(s),), s.dtype, context=context)
         host[:] = s
         pinned_slices.append(host.view(np.recarray))
+    resident = _resident(queue, pinned_slices)
+    resident.wait()
 
     def step_resident():
-        imager.clear_dirty()
-        for w_slice, entry in enumerate(resident):
-            if entry is None:
-                continue
-            n, bufs = entry
-            imager.clear_grid()
-            imager.bind(**bufs)
-            imager.num_vis = n
-            imager.grid()
-            imager.grid_to_image(mid_w[w_slice])
-
-    def step_e2e(im, out):
-        """One channel through the Imaging facade from pinned HOST records to a pinned HOST
-        dirty image; everything is enqueued on the imager's own queue, nothing waits."""
-        im.clear_dirty()
-        for w_slice, s in enumerate(pinned_slices):
-            if len(s) == 0:
-                continue
-            im.clear_grid()
-            for start in range(0, len(s), VIS_BLOCK):
-                chunk = s[start:start + VIS_BLOCK]
-                im.num_vis = len(chunk)
-                im.set_coordinates(chunk)
-                im.set_vis(chunk.vis)
-                im.grid()
-            im.grid_to_image(mid_w[w_slice])
-        im.buffer('dirty').get_async(im.command_queue, out)
+        return pipeline.process_channel(imager, resident, ip, gp, cp, wp, MAJOR, VIS_BLOCK)
 
     # ---- FP32 roofline denominator: FFMA micro-benchmark on all SMs
     sink = accel.DeviceArray(context, (1,), np.float32)
@@ -396,8 +485,9 @@ def run_gpu(args, ranks):
 
     # ---- timed region: K steps with resident inputs
     sampler = ClockSampler(ranks.local_rank)        # already streaming when the timed region starts
+    stats = None
     for _ in range(args.warmup):
-        step_resident()
+        stats = step_resident()
     queue.finish()
     ranks.barrier()
     sampler.mark_start()
@@ -406,7 +496,7 @@ def run_gpu(args, ranks):
     launches0 = _lib.kernel_launches
     start = queue.enqueue_marker()
     for _ in range(args.steps):
-        step_resident()
+        stats = step_resident()
     stop = queue.enqueue_marker()
     stop.wait()
     queue.finish()
@@ -418,123 +508,174 @@ def run_gpu(args, ranks):
     clocks = sampler.stop()
     seconds = ranks.max(seconds)
     per_kernel = timer.device_seconds()
-    grid_calls = [stop_.time_since(start_) for start_, stop_ in timer.records.get('grid', [])]
-    slices_per_step = max(1, len(grid_calls) // args.steps)
-    grid_ms_per_slice = [1e3 * float(np.mean(grid_calls[i::slices_per_step]))
-                         for i in range(slices_per_step)]
     step_seconds = seconds / args.steps
-    value = total_vis * ranks.world / step_seconds
+    value = work['gridded_vis'] * ranks.world / step_seconds
+    resident_image = imager.get_buffer('dirty')
 
-    # ---- e2e: host buffers through the Imaging facade.  E2E_DEPTH imagers on their own command
-    # queues take channels in turn (imaging.ImagingPipeline), so the record upload and image
-    # download of one step overlap the kernels of the next; every step still copies all of
-    # its inputs from pinned host memory and its dirty image back to the host.
-    queue.finish()
-    pipeline = imaging.ImagingPipeline(template, E2E_DEPTH, ip, gp, VIS_BLOCK, 0, 1)
-    dirty_host = []
-    for im in pipeline.imagers:
-        im.clear_weights()
-        im.finalize_weights()
-        dirty_host.append(im.buffer('dirty').empty_like())
-    for _ in range(len(pipeline)):      # warm-up (first touch, scratch allocation)
-        slot, im = pipeline.acquire()
-        step_e2e(im, dirty_host[slot])
-        pipeline.release(slot)
-    pipeline.finish()
+    # ---- e2e: pinned host records -> device once per step, image the channel, final image in
+    # FITS order straight into this rank's plane of a cube file shared by all ranks
+    cube_dir = os.environ.get('KIB_CUBE_DIR') or ('/dev/shm' if os.path.isdir('/dev/shm')
+                                                  else tempfile.gettempdir())
+    cube_name = os.path.join(cube_dir, 'kib_bench_cube_{}.fits'.format(
+        os.environ.get('MASTER_PORT', str(os.getpid()))))
+    if ranks.rank == 0:
+        io.FitsCube.create(cube_name, ranks.world, ip, 299792458.0 / ip.wavelength,
+                           856e6 / NUM_CHANNELS).close()
     ranks.barrier()
-    e2e_steps = args.steps
-    t0 = pipeline.queues[0].enqueue_marker()
-    ends = []
-    for _ in range(e2e_steps):
-        slot, im = pipeline.acquire()
-        step_e2e(im, dirty_host[slot])
-        ends.append(pipeline.release(slot))
-    pipeline.finish()
-    e2e_seconds = ranks.max(max(e.time_since(t0) for e in ends[-len(pipeline):])) / e2e_steps
-    e2e_check = float(dirty_host[0][0, PIXELS // 2, PIXELS // 2])
-    h2d = total_vis * slices[0].dtype.itemsize      # whole 60-byte records are uploaded
-    d2h = dirty_host[0].nbytes
+    cube = io.FitsCube(cube_name)
+    cube.pin(ranks.rank, ranks.rank + 1)
+    e2e_vis = _resident(queue, pinned_slices)       # allocates; every step re-uploads into it
 
-    # ---- rooflines.  `roofline` is the kernel that takes most of the step, the row pass of the
-    # fused grid -> image transform (HBM roofline over its ALGORITHMIC bytes: the half-transformed
-    # plane read once, the image plane read and written once); the column pass and the gridder
-    # (FP32 pipe, the north star's named kernel) follow as extra objects.
-    grid_count, grid_seconds = per_kernel.get('grid', (0, 0.0))
-    grid_launch = grid_seconds / max(grid_count, 1)
-    vis_per_launch = total_vis * args.steps / max(grid_count, 1)
-    achieved = vis_per_launch * flops_per_vis(KERNEL_WIDTH, POLS) / grid_launch / 1e12
+    def step_e2e():
+        e2e_vis.upload(pinned_slices)
+        pipeline.process_channel(imager, e2e_vis, ip, gp, cp, wp, MAJOR, VIS_BLOCK)
+        cube.store_device(ranks.rank, imager.buffer('dirty'), queue)
+
+    step_e2e()
+    queue.finish()
+    ranks.barrier()
+    t0 = queue.enqueue_marker()
+    for _ in range(args.steps):
+        step_e2e()
+    t1 = queue.enqueue_marker()
+    t1.wait()
+    queue.finish()
+    e2e_seconds = ranks.max(t1.time_since(t0)) / args.steps
+    h2d = e2e_vis.h2d_bytes
+    d2h = int(np.prod(cube.shape[1:])) * 4
+    # the e2e image (read back from the cube file) against the resident-path image
+    e2e_image = np.array(cube.plane(ranks.rank)).astype(np.float32)[:, :, ::-1]
+    peak = float(np.abs(resident_image).max())
+    diff = e2e_image - resident_image
+    parity = {'e2e_vs_resident': {
+        'rms_rel_peak': float(np.sqrt(np.mean(diff.astype(np.float64) ** 2)) / peak),
+        'max_rel_peak': float(np.abs(diff).max() / peak), 'bar': 1e-4,
+        'note': 'final image from the cube file (FITS order undone) against the image of the '
+                'resident-records run; gridding uses atomics, so two runs agree to rounding'}}
+    del e2e_image, diff
+    cube.close()
+    ranks.barrier()
+    if ranks.rank == 0:
+        try:
+            os.unlink(cube_name)
+        except OSError:
+            pass
+
+    # ---- rooflines
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_file):
         hbm_peak, hbm_source = json.load(open(peaks_file))['hbm_gbs'], 'MEASURED_PEAKS.json'
     else:
         hbm_peak, hbm_source = 6650.0, 'fallback (B200_PROFILING.md)'
-    traffic_file = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    traffic_file = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
-    grid_traffic = (traffic['grid_dram_bytes_per_vis'] * vis_per_launch
-                    if 'grid_dram_bytes_per_vis' in traffic else None)
     grid_size = imager.buffer('grid').shape[-1]
+    G, N = float(grid_size), float(PIXELS)
 
     def hbm_roofline(name, kernel, nbytes, traffic_key, note):
-        count, seconds = per_kernel.get(name, (0, 0.0))
+        count, secs = per_kernel.get(name, (0, 0.0))
         if not count:
             return None
-        gbs = nbytes / (seconds / count) / 1e9
-        return {'kernel': kernel, 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak,
-                'unit': 'GB/s', 'frac': gbs / hbm_peak, 'traffic': traffic.get(traffic_key),
-                'peak_source': hbm_source, 'bytes_per_launch': nbytes,
-                'avg_launch_ms': seconds / count * 1e3, 'launches_per_step': count / args.steps,
+        gbs = nbytes / (secs / count) / 1e9
+        return {'kernel': kernel, 'label': name, 'bound': 'hbm', 'achieved': gbs,
+                'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                'traffic': traffic.get(traffic_key), 'peak_source': hbm_source,
+                'bytes_per_launch': nbytes, 'avg_launch_ms': secs / count * 1e3,
+                'launches_per_step': count / args.steps, 'ms_per_step': secs / args.steps * 1e3,
                 'note': note}
+
+    def fp32_roofline(name, kernel, vis_per_step, traffic_key, bytes_per_vis):
+        count, secs = per_kernel.get(name, (0, 0.0))
+        if not count:
+            return None
+        vis_per_launch = vis_per_step * args.steps / count
+        tflops = vis_per_launch * flops_per_vis(KERNEL_WIDTH, POLS) / (secs / count) / 1e12
+        per_vis = traffic.get(traffic_key)
+        return {'kernel': kernel, 'label': name, 'bound': 'fp32', 'achieved': tflops,
+                'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s', 'frac': tflops / (fp32_peak / 1e12),
+                'traffic': per_vis * vis_per_launch if per_vis else None,
+                'peak_source': 'FFMA micro-benchmark run in this process (burst); nominal 74.5',
+                'flops_per_vis': flops_per_vis(KERNEL_WIDTH, POLS),
+                'algorithmic_bytes_per_vis': bytes_per_vis, 'vis_per_launch': vis_per_launch,
+                'vis_per_sec': vis_per_launch / (secs / count),
+                'avg_launch_ms': secs / count * 1e3, 'ms_per_step': secs / args.steps * 1e3}
 
     rows_roofline = hbm_roofline(
         'grid_to_image_rows', 'rows_kernel<8192,256,16,16,2> (kib_gridfft.cu)',
-        8.0 * PIXELS * grid_size + 8.0 * PIXELS * PIXELS, 'fused_rows_dram_bytes_per_launch',
-        'algorithmic bytes = 8 N G (half-transformed plane) + 8 N^2 (image read + write); the '
-        'kernel is issue-bound (77 % of issue slots busy, profiles/r01_fused_fft_ncu_summary.csv)')
-    columns_roofline = hbm_roofline(
-        'grid_to_image_columns', 'columns_kernel (kib_gridfft.cu)',
-        8.0 * grid_size * grid_size + 8.0 * PIXELS * grid_size,
-        'fused_columns_dram_bytes_per_launch',
-        'algorithmic bytes = 8 G^2 (grid plane) + 8 N G (half-transformed plane written)')
-    epilogue_roofline = hbm_roofline(
-        'layer_to_image', 'layer_to_image_x2_kernel (kib_image.cu; cuFFT route only)',
-        16.0 * PIXELS * PIXELS, 'layer_to_image_dram_bytes_per_launch',
-        '16 B per pixel: layer read, image read + write')
-    gridder_roofline = {
-        'kernel': 'grid_stage_kernel<4> + grid_tma_kernel<float,4,7,1> (kib_grid.cu)',
-        'bound': 'fp32',
-        'achieved': achieved, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
-        'frac': achieved / (fp32_peak / 1e12), 'traffic': grid_traffic,
-        'traffic_note': 'DRAM bytes per launch from the committed ncu capture '
-                        '(profiles/r01_traffic.json), scaled to the average launch; '
-                        'algorithmic bytes are 58 B/vis, the staged records add 96 B/vis',
-        'peak_source': 'FFMA micro-benchmark run in this process (burst); nominal 74.5',
-        'flops_per_vis': flops_per_vis(KERNEL_WIDTH, POLS),
-        'vis_per_launch': vis_per_launch, 'avg_launch_ms': grid_launch * 1e3}
+        8.0 * N * G + 8.0 * N * N, 'fused_rows_dram_bytes_per_launch',
+        'algorithmic bytes = 8 N G (half-transformed plane) + 8 N^2 (image read + write)')
+    rooflines = {
+        'grid_to_image_columns': hbm_roofline(
+            'grid_to_image_columns', 'columns_cluster_kernel<8,1024,8> (kib_gridfft.cu)',
+            8.0 * G * G + 8.0 * N * G, 'fused_columns_dram_bytes_per_launch',
+            'algorithmic bytes = 8 G^2 (grid plane) + 8 N G (half-transformed plane written)'),
+        'image_to_grid_rows': hbm_roofline(
+            'image_to_grid_rows', 'rows_fwd_kernel<8192,256,16,16,2> (kib_gridfft.cu)',
+            4.0 * N * N + 8.0 * N * G, 'fused_rows_fwd_dram_bytes_per_launch',
+            'algorithmic bytes = 4 N^2 (image read) + 8 N G (half-transformed plane written)'),
+        'image_to_grid_columns': hbm_roofline(
+            'image_to_grid_columns', 'columns_fwd_kernel + unfold_kernel (kib_gridfft.cu)',
+            8.0 * N * G + 8.0 * G * G, 'fused_columns_fwd_dram_bytes_per_launch',
+            'algorithmic bytes = 8 N G (read) + 8 G^2 (grid plane written)'),
+        'gridder': fp32_roofline(
+            'grid', 'grid_stage_kernel<4> + grid_tma_kernel<float,4,7,1> (kib_grid.cu)',
+            work['gridded_vis'], 'grid_dram_bytes_per_vis', 10 + 12 * POLS),
+        'degridder': fp32_roofline(
+            'degrid', 'degrid_kernel (kib_degrid.cu)', work['degridded_vis'],
+            'degrid_dram_bytes_per_vis', 10 + 20 * POLS),
+    }
+    clean_count, clean_secs = per_kernel.get('clean_cycles', (0, 0.0))
+    patch = stats.get('psf_patch_size', (0, 0))
+    if clean_count and stats.get('minor'):
+        cycles = (stats['minor'] - stats['major']) * args.steps     # batched cycles only
+        nbytes = 12.0 * patch[0] * patch[1] * POLS
+        gbs = nbytes * cycles / clean_secs / 1e9
+        rooflines['clean'] = {
+            'kernel': 'clean_persistent_kernel<4, SUMSQ> (kib_clean.cu)', 'label': 'clean_cycles',
+            'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': gbs / hbm_peak, 'traffic': None, 'peak_source': hbm_source,
+            'bytes_per_cycle': nbytes, 'cycles_per_sec': cycles / clean_secs,
+            'us_per_cycle': clean_secs / cycles * 1e6, 'patch': list(patch),
+            'ms_per_step': clean_secs / args.steps * 1e3,
+            'note': '12 B per patch pixel and polarization (psf read, dirty read + write); the '
+                    'patch is L2-resident between cycles, the cycle is a chain of dependent '
+                    'L2 round trips (DESIGN.md section 4.4)'}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ranks.world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_seconds * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(total_vis, args, ranks.world),
         'clocks': clocks, 'gpu_launches': launches,
-        'e2e': {'value': total_vis * ranks.world / e2e_seconds, 'unit': UNIT,
+        'channels_imaged_per_sec': ranks.world / step_seconds,
+        'e2e': {'value': work['gridded_vis'] * ranks.world / e2e_seconds, 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': e2e_seconds * 1e3, 'steps': e2e_steps,
-                'queues_in_flight': E2E_DEPTH, 'centre_pixel': e2e_check},
-        'roofline': rows_roofline if rows_roofline is not None else epilogue_roofline,
-        'roofline_columns': columns_roofline,
-        'roofline_gridder': gridder_roofline,
+                'ms_per_step': e2e_seconds * 1e3, 'steps': args.steps,
+                'channels_imaged_per_sec': ranks.world / e2e_seconds,
+                'output': 'FITS-ordered planes written by the device into a cube file mapped by '
+                          'all ranks ({})'.format(cube_dir)},
+        'step_stats': {k: (list(v) if isinstance(v, tuple) else
+                           (float(v) if isinstance(v, (np.floating, float)) else v))
+                       for k, v in stats.items()},
+        'work_per_step': work,
+        'roofline': rows_roofline,
+        'rooflines': {k: v for k, v in rooflines.items() if v is not None},
         'kernels_ms_per_step': {k: v[1] / args.steps * 1e3 for k, v in sorted(per_kernel.items())},
-        'channels_per_sec': ranks.world / step_seconds,
-        'grid_ms_per_slice': grid_ms_per_slice,
-        'vis_per_slice': [len(s) for s in slices if len(s)],
+        'parity': parity,
     }
     if ranks.rank == 0:
         if ranks.world == 1 and not args.no_cpu:
+            line['parity']['plane_vs_oracle'] = oracle_plane_check(imager, ip, gp, slices,
+                                                                   mid_w, queue)
             threads = os.cpu_count() or 1
-            rate, _, sample, extra = cpu_channel_rate(ip, gp, slices, threads, args.cpu_vis,
-                                                      max(1, min(threads, args.cpu_planes)))
-            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads,
-                                    'kind': 'port', 'sample': sample, **extra}
+            sample = CpuSample(ip, gp, slices, threads, args.cpu_fraction)
+            sample.run() if args.cpu_warm else None
+            t = sample.run()
+            sample.close()
+            rate = args.cpu_fraction * work['gridded_vis'] / t['total']
+            line['cpu_baseline'] = {
+                'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                'sample': sample.description, 'sample_seconds': t['total'],
+                'stage_seconds': t, 'channels_imaged_per_sec': args.cpu_fraction / t['total']}
         print(json.dumps(line), flush=True)
 
 
@@ -542,16 +683,17 @@ def main():
     parser = argparse.ArgumentParser(description=__doc__,
                                      formatter_class=argparse.RawDescriptionHelpFormatter)
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=20)
+    parser.add_argument('--steps', type=int, default=10)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     parser.add_argument('--dumps', type=int, default=3600,
                         help='time samples per baseline (2016 baselines; 3600 -> 7.26 Mvis)')
-    parser.add_argument('--cpu-vis', type=int, default=150000,
-                        help='visibilities per host thread in the CPU sample')
-    parser.add_argument('--cpu-planes', type=int, default=4,
-                        help='image planes in the CPU sample')
-    parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    parser.add_argument('--cpu-fraction', type=float, default=1.0 / 80,
+                        help='fraction of one channel the CPU sample executes per step')
+    parser.add_argument('--cpu-warm', action='store_true',
+                        help='run the CPU sample twice in the cpu_baseline leg, report the second')
+    parser.add_argument('--no-cpu', action='store_true',
+                        help='skip the cpu_baseline leg and the oracle parity check')
     args = parser.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3

@@ -79,6 +79,10 @@ int kib_malloc(void **ptr, size_t bytes);
 int kib_free(void *ptr);
 int kib_host_alloc(void **ptr, size_t bytes);   /* pinned host memory */
 int kib_host_free(void *ptr);
+/* Page-lock an existing host range (e.g. the mapping of an output file) so that device copies
+ * can target it directly; kib_host_unregister before unmapping it. */
+int kib_host_register(void *ptr, size_t bytes);
+int kib_host_unregister(void *ptr);
 int kib_memset_async(void *ptr, int value, size_t bytes, kib_stream_t stream);
 int kib_memcpy_h2d_async(void *dst, const void *src, size_t bytes, kib_stream_t stream);
 int kib_memcpy_d2h_async(void *dst, const void *src, size_t bytes, kib_stream_t stream);
@@ -355,6 +359,11 @@ int kib_mean_weight(const float *grid, int row_stride, int width, int height,
  * (device double[3]). */
 int kib_density_weights(float *grid, int row_stride, int64_t pol_stride, int width, int height,
                         int num_pols, float a, float b, double *sums, kib_stream_t stream);
+/* kib_fits_plane writes an image in the order the reference's FITS writer stores it
+ * (io.py:186-200: l axis reversed, big-endian, rows packed): out[p][y][x] =
+ * byteswap(image[p][y][width-1-x]).  float32 only. */
+int kib_fits_plane(void *out, const void *image, int row_stride, int64_t pol_stride,
+                   int width, int height, int num_pols, int dtype, kib_stream_t stream);
 /* kib_fill: katsdpsigproc.fill.FillTemplate (weight.py:403,480-484). */
 int kib_fill(void *data, int row_stride, int64_t pol_stride, int width, int height,
              int num_pols, double value, int dtype, kib_stream_t stream);

@@ -497,12 +497,12 @@ clean_step_kernel(const CleanStepParams prm)
 //     parallel load of candidates (row maxima of untouched tile rows, tiles of touched rows);
 //   * the next peak travels to the other blocks as two self-validating 16-byte packets
 //     {cycle, y << 16 | x, value, pixel[0]}, {cycle, pixel[1..3]} that they poll with acquire
-//     loads -- no separate flag; polling is relaxed, with one acquire fence per cycle and block.
+//     loads -- no separate flag, no fence on the critical path.
 // state: [0] cycles done, [1] stopped by threshold, [2] arrivals, [4..7] / [8..11] packets.
-__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 *p)
+__device__ __forceinline__ uint4 ld_acquire_v4(const uint4 *p)
 {
     uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
@@ -511,10 +511,10 @@ __device__ __forceinline__ void st_release_v4(uint4 *p, uint4 v)
     asm volatile("st.release.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ int atom_add_release(int *p, int v)
+__device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
 {
     int old;
-    asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
     return old;
 }
 
@@ -541,13 +541,12 @@ clean_persistent_kernel(const CleanStepParams prm)
                     s_peak[3 + p] = __float_as_uint(__ldcg(static_cast<const Real *>(prm.peak_pixel) + p));
             } else {
                 uint4 a, b;
-                // relaxed polling (an acquire load would invalidate this SM's L1 on every
-                // iteration), one acquire fence once the packets of this cycle are in
+                // (relaxed polling followed by one fence measured slower: 8.6 against 7.9 us
+                // per cycle at a 255^2 patch)
                 do {
-                    a = ld_relaxed_v4(packets);
-                    b = P > 1 ? ld_relaxed_v4(packets + 1) : a;
+                    a = ld_acquire_v4(packets);
+                    b = P > 1 ? ld_acquire_v4(packets + 1) : a;
                 } while (a.x != (unsigned) done || b.x != (unsigned) done);
-                __threadfence();
                 s_peak[0] = a.y >> 16;
                 s_peak[1] = a.y & 0xffffu;
                 s_peak[2] = a.z;
@@ -576,10 +575,7 @@ clean_persistent_kernel(const CleanStepParams prm)
         if (blockIdx.x == 0 && threadIdx.x == 0) clean_record<Real, P>(prm, g, scale, pv, done);
         // ---- arrive; the last arrival finds the next peak and publishes it
         __syncthreads();
-        if (threadIdx.x == 0) {
-            is_last = atom_add_release(state + 2, 1) == nblocks - 1;
-            if (is_last) __threadfence();
-        }
+        if (threadIdx.x == 0) is_last = atom_add_acq_rel(state + 2, 1) == nblocks - 1;
         __syncthreads();
         if (!is_last) continue;
 

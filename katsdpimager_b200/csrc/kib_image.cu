@@ -308,6 +308,22 @@ fill_kernel(Real *__restrict__ data, int row_stride, long long pol_stride, int w
         data[addr] = value;
 }
 
+// FITS plane order (reference io.py:186-200): the l axis reversed (RA increases to the left)
+// and every value big-endian, packed rows.  Done on the device so that the D2H copy can land
+// directly in the output file's mapping.
+__global__ void __launch_bounds__(256)
+fits_plane_kernel(unsigned *__restrict__ out, const unsigned *__restrict__ image, int row_stride,
+                  long long pol_stride, int width, int height, int num_pols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= width) return;
+    const long long in = (long long) y * row_stride + (width - 1 - x);
+    const long long o = (long long) y * width + x;
+    for (int p = 0; p < num_pols; p++)
+        out[p * (long long) width * height + o] = __byte_perm(image[p * pol_stride + in], 0, 0x0123);
+}
+
 static dim3 row_grid(int width, int height) { return dim3(divup(width, 256), height, 1); }
 
 }  // namespace kib
@@ -489,6 +505,18 @@ int kib_apply_primary_beam(void *image, int row_stride, int64_t pol_stride,
             static_cast<double *>(image), row_stride, pol_stride,
             static_cast<const double *>(beam_power), width, height, num_pols,
             threshold, replacement);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_fits_plane(void *out, const void *image, int row_stride, int64_t pol_stride,
+                   int width, int height, int num_pols, int dtype, kib_stream_t stream)
+{
+    KIB_REQUIRE(dtype == KIB_F32, "kib_fits_plane: only float32 images are supported");
+    if (width <= 0 || height <= 0) return 0;
+    fits_plane_kernel<<<row_grid(width, height), 256, 0, as_stream(stream)>>>(
+        static_cast<unsigned *>(out), static_cast<const unsigned *>(image), row_stride,
+        pol_stride, width, height, num_pols);
     KIB_CHECK_LAUNCH();
     return 0;
 }

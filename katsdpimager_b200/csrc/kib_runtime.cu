@@ -235,6 +235,19 @@ int kib_host_free(void *ptr)
     return 0;
 }
 
+int kib_host_register(void *ptr, size_t bytes)
+{
+    KIB_REQUIRE(ptr != nullptr && bytes > 0, "kib_host_register: empty range");
+    KIB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int kib_host_unregister(void *ptr)
+{
+    KIB_CUDA(cudaHostUnregister(ptr));
+    return 0;
+}
+
 int kib_memset_async(void *ptr, int value, size_t bytes, kib_stream_t stream)
 {
     if (bytes == 0) return 0;

@@ -61,3 +61,29 @@ def gather_planes(planes, channels, num_channels, dist=None, dst=0):
                 cube = np.full((num_channels,) + a.shape, np.nan, a.dtype)
             cube[c] = a
     return cube
+
+
+def image_channel_block(template, command_queue, channels, load_channel, cube, major, vis_block,
+                        weight_parameters, restore=None):
+    """Image the channels of this rank's block and store each finished plane in `cube`
+    (a :class:`~.io.FitsCube` mapped by every rank): the channel loop of reference
+    frontend.py:749-767 restricted to ``channels``, one :func:`~.pipeline.process_channel`
+    per channel, visibilities uploaded once per channel.
+
+    ``load_channel(channel)`` returns ``(image_parameters, grid_parameters, slices)`` with
+    `slices` the preprocessed records per W slice.  Returns {channel: statistics}.
+    """
+    from . import pipeline
+    stats = {}
+    pols = len(template.fixed_image_parameters.polarizations)
+    for channel in channels:
+        ip, gp, slices = load_channel(channel)
+        imager = template.instantiate(command_queue, ip, gp, vis_block, 0, major)
+        imager.ensure_all_bound()
+        vis = pipeline.ResidentVisibilities(command_queue, slices, pols)
+        stats[channel] = pipeline.process_channel(
+            imager, vis, ip, gp, template.clean_parameters, weight_parameters, major, vis_block,
+            restore=restore)
+        cube.store_device(channel, imager.buffer('dirty'), command_queue)
+        command_queue.finish()
+    return stats

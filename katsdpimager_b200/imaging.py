@@ -338,6 +338,33 @@ class Imaging(accel.OperationSequence):
         else:
             self._set_buffer('weights', N, weights)
 
+    # ------------------------------------------------ visibilities resident in HBM
+    @profile_function()
+    def set_resident(self, resident, w_slice, start, count, field='vis', with_weights=False):
+        """Equivalent of ``num_vis = count; set_coordinates(chunk); set_vis(chunk[field])``
+        (and ``set_weights(chunk.weights)`` with `with_weights`) for records
+        [start, start + count) of W slice `w_slice` of a
+        :class:`~.pipeline.ResidentVisibilities`: the fields are unpacked from device memory,
+        nothing crosses PCIe."""
+        if field not in ('vis', 'weights'):
+            raise ValueError('field must be vis or weights')
+        self.num_vis = count
+        self._records.invalidate()
+        resident.unpack(self.command_queue, w_slice, start, count,
+                        uv=self.buffer('uv'), w_plane=self.buffer('w_plane'),
+                        weights=self.buffer('weights') if with_weights else None,
+                        vis=self.buffer('vis'), vis_from_weights=field == 'weights')
+
+    @profile_function()
+    def grid_weights_resident(self, resident, w_slice, start, count):
+        """:meth:`grid_weights` for resident records."""
+        if count > self._gridder.max_vis:
+            raise ValueError('chunk is larger than max_vis')
+        self._records.invalidate()
+        resident.unpack(self.command_queue, w_slice, start, count,
+                        uv=self.buffer('uv'), weights=self.buffer('weights'))
+        self._weights.grid(count)
+
     # ----------------------------------------------------------------------- weights
     @profile_function()
     def clear_weights(self):

@@ -1,0 +1,259 @@
+"""Imaging one channel with the visibilities resident in HBM.
+
+Host-side mirror of the reference's per-channel driver ``frontend.process_channel``
+(reference frontend.py:465-658) and its helpers ``make_weights`` (:86-107) and
+``make_dirty`` (:110-149), minus everything that is I/O (FITS writer, progress bars,
+telstate statistics) -- same call sequence on the :class:`~.imaging.Imaging` facade, same
+thresholds, same skipping of empty W slices.
+
+What differs is where the visibilities live.  The reference re-reads every chunk from the
+host store and uploads it again on every pass (weights, PSF, every major cycle:
+frontend.py:128-138, imaging.py:269-314); on B200 that PCIe traffic costs more than all the
+kernels.  Here :class:`ResidentVisibilities` uploads the preprocessed records of a channel
+ONCE (array of structures, exactly as the preprocessor emits them, reference
+preprocess.cpp:39-52) and every pass unpacks the fields it needs from device memory
+(``kib_unpack_records``).  The records are never modified -- prediction subtracts from the
+unpacked copy, as in the reference -- so any number of passes can replay them.
+
+The minor cycles of a major cycle run as one device-resident batch
+(:meth:`~.imaging.Imaging.clean_cycles`); the sequence of components is identical to calling
+``clean_cycle`` in a loop as the reference does (frontend.py:577-582).
+"""
+import numpy as np
+
+from . import _lib, accel, clean, weight
+from .profiling import profile_device
+
+
+class ResidentVisibilities:
+    """Preprocessed visibility records of one channel, one device array per W slice.
+
+    `slices` is a sequence of contiguous record arrays (fields ``uv, sub_uv, w_plane,
+    weights, vis``; one entry per W slice, possibly empty).  Uploads are enqueued on
+    `command_queue`; pinned arrays (:class:`~.accel.HostArray`) are copied without staging.
+    """
+
+    def __init__(self, command_queue, slices, num_polarizations):
+        self.command_queue = command_queue
+        self.num_polarizations = num_polarizations
+        self.record_bytes = 12 + 12 * num_polarizations
+        self.counts = [len(s) for s in slices]
+        context = command_queue.context
+        self.device = [accel.DeviceArray(context, (n * self.record_bytes,), np.uint8) if n else None
+                       for n in self.counts]
+        self.h2d_bytes = 0
+        self._keepalive = []
+        self._uploaded = None
+        self.upload(slices)
+
+    def upload(self, slices):
+        """(Re-)upload the records; `slices` must have the lengths given at construction."""
+        if [len(s) for s in slices] != self.counts:
+            raise ValueError('slice lengths differ from those this object was built for')
+        queue = self.command_queue
+        keepalive = []
+        self.h2d_bytes = 0
+        for records, dev in zip(slices, self.device):
+            if dev is None:
+                continue
+            if records.dtype.itemsize != self.record_bytes or not records.flags.c_contiguous:
+                raise TypeError('records must be contiguous {}-byte structures'.format(
+                    self.record_bytes))
+            nbytes = len(records) * self.record_bytes
+            raw = records.view(np.uint8).reshape(-1)
+            if not accel.is_pinned(records):
+                pinned = accel.HostArray((nbytes,), np.uint8, context=queue.context)
+                pinned[:] = raw
+                raw = pinned
+            _lib.call('kib_memcpy_h2d_async', dev.ptr, raw.ctypes.data, nbytes, queue.stream)
+            keepalive.append(raw)
+            self.h2d_bytes += nbytes
+        if self._uploaded is not None and self._keepalive:
+            self._uploaded.wait()           # staging of the previous upload may go now
+        self._keepalive = keepalive
+        self._uploaded = queue.enqueue_marker()
+
+    @property
+    def num_w_slices(self):
+        return len(self.counts)
+
+    def __len__(self):
+        return sum(self.counts)
+
+    def len(self, w_slice):
+        return self.counts[w_slice]
+
+    def wait(self):
+        """Block until the uploads have completed (the host arrays may then be reused)."""
+        self._uploaded.wait()
+        self._keepalive = []
+
+    def chunks(self, w_slice, block_size):
+        """(start, count) pairs covering the slice in chunks of at most `block_size`."""
+        n = self.counts[w_slice]
+        for start in range(0, n, block_size):
+            yield start, min(block_size, n - start)
+
+    def unpack(self, queue, w_slice, start, count, uv=None, w_plane=None, weights=None,
+               vis=None, vis_from_weights=False):
+        """Split records [start, start + count) of a slice into per-field device buffers."""
+        def ptr(buffer):
+            return buffer.ptr if buffer is not None else None
+        base = (self.device[w_slice].ptr.value or 0) + start * self.record_bytes
+        with profile_device(queue, 'unpack_records'):
+            _lib.call('kib_unpack_records', base, self.record_bytes, count,
+                      self.num_polarizations, ptr(uv), ptr(w_plane), ptr(weights), ptr(vis),
+                      int(vis_from_weights), queue.stream)
+
+
+    def feed(self, imager, w_slice, start, count, field, with_weights):
+        """Make records [start, start + count) the imager's current chunk."""
+        imager.set_resident(self, w_slice, start, count, field, with_weights)
+
+    def feed_weights(self, imager, w_slice, start, count):
+        imager.grid_weights_resident(self, w_slice, start, count)
+
+
+class HostVisibilities:
+    """The same interface over host record arrays, chunk by chunk through the reference's
+    calls (``set_coordinates`` / ``set_vis`` / ``set_weights`` / ``grid_weights``): every
+    pass uploads every chunk again, as reference frontend.py:128-138 does."""
+
+    def __init__(self, slices):
+        self.slices = [s.view(np.recarray) for s in slices]
+        self.counts = [len(s) for s in slices]
+
+    @property
+    def num_w_slices(self):
+        return len(self.counts)
+
+    def __len__(self):
+        return sum(self.counts)
+
+    def len(self, w_slice):
+        return self.counts[w_slice]
+
+    chunks = ResidentVisibilities.chunks
+
+    def feed(self, imager, w_slice, start, count, field, with_weights):
+        chunk = self.slices[w_slice][start:start + count]
+        imager.num_vis = count
+        imager.set_coordinates(chunk)
+        imager.set_vis(chunk[field])
+        if with_weights:
+            imager.set_weights(chunk.weights)
+
+    def feed_weights(self, imager, w_slice, start, count):
+        chunk = self.slices[w_slice][start:start + count]
+        imager.grid_weights(np.array(chunk.uv), chunk.weights)
+
+
+def make_weights(imager, vis, weight_type, vis_block):
+    """reference frontend.make_weights (frontend.py:86-107)."""
+    imager.clear_weights()
+    if weight_type != weight.WeightType.NATURAL:
+        for w_slice in range(vis.num_w_slices):
+            for start, count in vis.chunks(w_slice, vis_block):
+                vis.feed_weights(imager, w_slice, start, count)
+    return imager.finalize_weights()
+
+
+def make_dirty(imager, vis, field, mid_w, vis_block, degrid, full_cycle=False):
+    """reference frontend.make_dirty (frontend.py:110-149) over resident records.
+
+    `field` is ``'weights'`` (PSF: the weights are gridded as visibilities,
+    frontend.py:511) or ``'vis'``."""
+    imager.clear_dirty()
+    if full_cycle and not degrid:
+        imager.model_to_predict()
+    for w_slice in range(vis.num_w_slices):
+        if vis.len(w_slice) == 0:
+            continue
+        if full_cycle and degrid:
+            imager.model_to_grid(mid_w[w_slice])
+        imager.clear_grid()
+        for start, count in vis.chunks(w_slice, vis_block):
+            vis.feed(imager, w_slice, start, count, field, full_cycle)
+            if full_cycle:
+                imager.predict(mid_w[w_slice])
+            imager.grid()
+        imager.grid_to_image(mid_w[w_slice])
+
+
+def process_channel(imager, vis, image_parameters, grid_parameters, clean_parameters,
+                    weight_parameters, major, vis_block, restore=None, out=None):
+    """reference frontend.process_channel (frontend.py:494-641) for one channel whose
+    visibilities are resident.
+
+    `restore`, if given, is called as ``restore(imager, psf_patch)`` after the last major
+    cycle and before the model is added back (the restoring-beam convolution,
+    frontend.py:623-636).  If `out` (pinned host array, polarizations x N x N) is given the
+    final image is copied into it asynchronously; call ``imager.command_queue.finish()``
+    before reading it.
+
+    Returns a dict of statistics (the quantities frontend.py:646-658 hands to the writer).
+    """
+    ip, gp, cp = image_parameters, grid_parameters, clean_parameters
+    degrid = bool(gp.fixed.degrid)
+    queue = imager.command_queue
+    num_pols = len(ip.fixed.polarizations)
+    stats = {'compressed_vis': len(vis), 'passes': 0}
+    if len(vis) == 0:
+        stats['skipped'] = 'no data'
+        return stats
+    imager.clear_model()
+    weights_noise, normalized_noise = make_weights(imager, vis, weight_parameters.weight_type,
+                                                   vis_block)
+    stats['weights_noise'] = weights_noise
+    stats['normalized_noise'] = normalized_noise
+
+    # PSF (frontend.py:507-540)
+    slice_w_step = float(gp.fixed.max_w / ip.wavelength / (gp.w_slices - 0.5))
+    mid_w = np.arange(gp.w_slices) * slice_w_step
+    make_dirty(imager, vis, 'weights', mid_w, vis_block, degrid)
+    stats['passes'] += 1
+    dirty = imager.buffer('dirty')
+    psf_peak = accel.HostArray((dirty.shape[0],), dirty.dtype, context=queue.context)
+    dirty.get_region(queue, psf_peak,
+                     np.s_[:, dirty.shape[1] // 2, dirty.shape[2] // 2], np.s_[:])
+    if np.any(psf_peak == 0):
+        stats['skipped'] = 'no usable data'
+        return stats
+    scale = np.reciprocal(psf_peak)
+    imager.scale_dirty(scale)
+    imager.dirty_to_psf()
+    psf_patch = imager.psf_patch()
+    stats['psf_patch_size'] = (psf_patch[2], psf_patch[1])
+
+    # major cycles (frontend.py:549-585)
+    stats['major'] = 0
+    stats['minor'] = 0
+    noise = None
+    for i in range(major):
+        make_dirty(imager, vis, 'vis', mid_w, vis_block, degrid, full_cycle=i != 0)
+        stats['passes'] += 1
+        imager.scale_dirty(scale)
+        stats['major'] += 1
+        noise = imager.noise_est()
+        imager.clean_reset()
+        peak_value = imager.clean_cycle(psf_patch)
+        peak_power = clean.metric_to_power(cp.mode, peak_value)
+        noise_threshold = noise * clean.noise_threshold_scale(cp.mode, cp.threshold, num_pols)
+        mgain_threshold = (1.0 - cp.major_gain) * peak_power
+        threshold = max(noise_threshold, mgain_threshold)
+        if peak_power <= threshold:
+            break
+        threshold_metric = clean.power_to_metric(cp.mode, threshold)
+        # frontend.py:577-582 counts the terminating call as a minor cycle too
+        values, stopped = imager.clean_cycles(psf_patch, threshold_metric, cp.minor - 1)
+        stats['minor'] += len(values) + (1 if stopped else 0)
+        if i == major - 1:
+            noise = imager.noise_est()
+    stats['noise'] = noise
+
+    if restore is not None:
+        restore(imager, psf_patch)
+    imager.add_model_to_dirty()
+    if out is not None:
+        imager.buffer('dirty').get_async(queue, out)
+    return stats

@@ -3,5 +3,13 @@ STOKES_I = 1
 STOKES_Q = 2
 STOKES_U = 3
 STOKES_V = 4
+STOKES_RR = 5
+STOKES_RL = 6
+STOKES_LR = 7
+STOKES_LL = 8
+STOKES_XX = 9
+STOKES_XY = 10
+STOKES_YX = 11
+STOKES_YY = 12
 STOKES_IQUV = [STOKES_I, STOKES_Q, STOKES_U, STOKES_V]
 STOKES_NAMES = [None, 'I', 'Q', 'U', 'V', 'RR', 'RL', 'LR', 'LL', 'XX', 'XY', 'YX', 'YY']

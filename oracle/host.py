@@ -188,6 +188,52 @@ def grid_to_image(grid_values, image, kernel1d, lm_scale, lm_bias, w):
     return image
 
 
+def grid_to_image_threaded(grid_plane, image_plane, kernel1d, lm_scale, lm_bias, w, pool, threads):
+    """:func:`grid_to_image` for ONE polarization plane with the work split over a thread
+    pool (row blocks): the same arithmetic per pixel (the 2-D transform as two 1-D passes), so the
+    result agrees to rounding (1e-7 of the peak, tests/test_oracle.py).  Used by bench.py's CPU legs so that the reference's single-threaded numpy
+    path (GridToImageHost, image.py:781-799) is timed on all host cores.
+
+    grid_plane : complex64 [G][G];  image_plane : float32 [N][N], accumulated into."""
+    pixels = image_plane.shape[-1]
+    full = _pad_grid(grid_plane[np.newaxis], pixels)[0]
+    layer = np.fft.ifftshift(full)
+    bounds = np.linspace(0, pixels, threads + 1).astype(int)
+    blocks = [(bounds[i], bounds[i + 1]) for i in range(threads) if bounds[i] < bounds[i + 1]]
+
+    def rows(block):
+        a, b = block
+        layer[a:b] = np.fft.ifft(layer[a:b], axis=1)
+
+    def cols(block):
+        a, b = block
+        layer[:, a:b] = np.fft.ifft(layer[:, a:b], axis=0)
+
+    list(pool.map(rows, blocks))
+    list(pool.map(cols, blocks))
+    scale = pixels * pixels
+    lm = np.arange(pixels).astype(image_plane.dtype) * lm_scale + lm_bias
+    lm = np.fft.ifftshift(lm)
+    lm2 = lm * lm
+    shifted = np.fft.ifftshift(np.arange(pixels))         # layer row r is image row shifted[r]
+    k1 = np.asarray(kernel1d)
+
+    def epilogue(block):
+        a, b = block
+        n = np.sqrt(1 - (lm2[a:b, np.newaxis] + lm2[np.newaxis, :]))
+        part = layer[a:b] * expj2pi(w * (n - 1))
+        out = part.real.copy()
+        out *= scale
+        out *= n
+        out = np.fft.fftshift(out, axes=1)
+        ys = shifted[a:b]
+        out /= np.outer(k1[ys], k1)
+        image_plane[ys] += out
+
+    list(pool.map(epilogue, blocks))
+    return image_plane
+
+
 def image_to_grid(image, kernel1d, lm_scale, lm_bias, w, complex_dtype=np.complex64,
                   grid_size=None):
     """ImageToGridHost.__call__; returns the (optionally centre-cropped) grid."""

@@ -212,3 +212,21 @@ def test_predict(oracle):
     # single-precision phases of hundreds of turns: the reference's own tolerance for
     # this routine is rtol 5e-4 (test_predict.py:92)
     np.testing.assert_allclose(vis, golden['residual'], rtol=5e-4, atol=5e-4)
+
+
+def test_grid_to_image_threaded_matches(oracle):
+    """The thread-pool variant used by bench.py's CPU legs equals grid_to_image."""
+    from concurrent.futures import ThreadPoolExecutor
+    rs = np.random.RandomState(1)
+    n, g = 256, 150
+    grid = (rs.standard_normal((1, g, g)) + 1j * rs.standard_normal((1, g, g))).astype(np.complex64)
+    taper = rs.uniform(1, 2, n).astype(np.float32)
+    lm_scale = 0.2 / n
+    lm_bias = -0.5 * n * lm_scale
+    expected = np.zeros((1, n, n), np.float32)
+    oracle.grid_to_image(grid, expected, taper, lm_scale, lm_bias, np.float64(31.5))
+    actual = np.zeros((n, n), np.float32)
+    with ThreadPoolExecutor(3) as pool:
+        oracle.grid_to_image_threaded(grid[0], actual, taper, lm_scale, lm_bias,
+                                      np.float64(31.5), pool, 3)
+    assert np.abs(actual - expected[0]).max() <= 1e-6 * np.abs(expected).max()
