@@ -216,7 +216,10 @@ int kib_grid_to_image(void *image_plane, int image_row_stride,
  *                              memory -> the grid_size columns the grid keeps -> scratch
  *                              (size rows of grid_size complex values).  factor_mode as in
  *                              kib_grid_to_image_rows (the factor here is
- *                              exp(-2 pi i w (n-1)) / (k1d[y] k1d[x] n));
+ *                              exp(-2 pi i w (n-1)) / (k1d[y] k1d[x] n)); factor_mode 3 =
+ *                              mode 0 plus: an image row that is entirely zero (a CLEAN
+ *                              model is zero almost everywhere) is answered with zeros
+ *                              without being transformed;
  *   kib_image_to_grid_columns  forward DFT along the rows of scratch, only for the
  *                              grid_size output rows the grid keeps -> grid_plane
  *                              (tile transforms into fold_scratch, then one butterfly

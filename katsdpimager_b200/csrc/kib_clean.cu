@@ -678,6 +678,12 @@ psf_patch_kernel(const Real *__restrict__ psf, int row_stride, long long pol_str
 }
 
 // ------------------------------------------------------------------- noise estimate
+// One radix digit of |pixel| (float bits) histogrammed over the region inside the border,
+// optionally restricted to values whose higher bits equal `prefix`.  Blocks walk whole image
+// rows (no per-element division); equal digits within a warp -- the common case for the
+// leading digit, where almost every value shares its exponent -- are combined with
+// match.any so that one lane adds the group's count (the shared-memory atomics of 32 lanes
+// on one bin used to serialise: 0.9 ms per pass at 8192^2 x 4, now memory-bound).
 __global__ void __launch_bounds__(256)
 abs_histogram_kernel(const float *__restrict__ image, int row_stride, long long pol_stride,
                      int inner_w, int inner_h, int P, int border,
@@ -687,17 +693,24 @@ abs_histogram_kernel(const float *__restrict__ image, int row_stride, long long 
     extern __shared__ unsigned local[];
     for (unsigned i = threadIdx.x; i <= mask; i += blockDim.x) local[i] = 0;
     __syncthreads();
-    const long long total = (long long) inner_w * inner_h * P;
-    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long) gridDim.x * blockDim.x) {
-        const int x = (int) (i % inner_w);
-        const long long r = i / inner_w;
-        const int y = (int) (r % inner_h);
-        const int p = (int) (r / inner_h);
-        const float v = image[p * pol_stride + (long long) (y + border) * row_stride + x + border];
-        const unsigned bits = __float_as_uint(fabsf(v));
-        if (!use_prefix || (bits >> prefix_shift) == prefix)
-            atomicAdd(&local[(bits >> shift) & mask], 1u);
+    const int lane = threadIdx.x & 31;
+    const int rows = inner_h * P;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int p = r / inner_h, y = r - p * inner_h;
+        const float *row = image + p * pol_stride + (long long) (y + border) * row_stride + border;
+#pragma unroll 4
+        for (int x0 = 0; x0 < inner_w; x0 += 256) {
+            const int x = x0 + threadIdx.x;
+            bool ok = x < inner_w;
+            const unsigned bits = ok ? __float_as_uint(fabsf(__ldg(row + x))) : 0u;
+            ok = ok && (!use_prefix || (bits >> prefix_shift) == prefix);
+            const unsigned bin = (bits >> shift) & mask;
+            const unsigned active = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const unsigned peers = __match_any_sync(active, bin);
+                if (lane == __ffs(peers) - 1) atomicAdd(&local[bin], (unsigned) __popc(peers));
+            }
+        }
     }
     __syncthreads();
     for (unsigned i = threadIdx.x; i <= mask; i += blockDim.x)
@@ -1027,11 +1040,9 @@ int kib_abs_histogram(const void *image, int row_stride, int64_t pol_stride,
     const int inner_w = width - 2 * border, inner_h = height - 2 * border;
     if (inner_w <= 0 || inner_h <= 0) return 0;
     const unsigned mask = (1u << bits) - 1;
-    const long long total = (long long) inner_w * inner_h * num_pols;
-    int blocks = (int) ((total + 256 * 16 - 1) / (256 * 16));
-    const int max_blocks = sm_count() * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
-    if (blocks < 1) blocks = 1;
+    const long long rows = (long long) inner_h * num_pols;
+    int blocks = sm_count() * 8;
+    if (blocks > rows) blocks = (int) rows;
     abs_histogram_kernel<<<blocks, 256, (mask + 1) * sizeof(unsigned), as_stream(stream)>>>(
         static_cast<const float *>(image), row_stride, pol_stride, inner_w, inner_h, num_pols,
         border, prefix, shift + bits, prefix_bits > 0, shift, mask, hist);

@@ -358,6 +358,10 @@ class ImageToGrid(accel.OperationSequence):
         self.slots['grid'] = accel.IOSlot(shape_grid, fft_plan.dtype_dest)
         #: use the fused pruned transform when the library supports the size
         self.fused = True
+        #: the image is a CLEAN model (zero except for a few hundred pixels): rows that are
+        #: entirely zero are not transformed.  Always exact; only the speed depends on it
+        #: (a dense image is transformed faster with False: shared per-pixel factors).
+        self.sparse_model = True
         self._factors = None
         self._fold = None
 
@@ -375,7 +379,7 @@ class ImageToGrid(accel.OperationSequence):
         n = layer.shape[1]
         context = self.command_queue.context
         factors = None
-        if polarizations > 1:
+        if polarizations > 1 and not self.sparse_model:
             if self._factors is None or self._factors.shape != (n, n):
                 self._factors = accel.DeviceArray(context, (n, n), grid.dtype)
             factors = self._factors.ptr
@@ -383,11 +387,15 @@ class ImageToGrid(accel.OperationSequence):
         if self._fold is None or self._fold.shape[0] < fold_bytes:
             self._fold = accel.DeviceArray(context, (fold_bytes,), np.uint8)
         for pol in range(polarizations):
+            if self.sparse_model:
+                mode = 3        # factor on the fly, all-zero image rows skipped
+            else:
+                mode = 0 if factors is None else (1 if pol == 0 else 2)
             with profile_device(self.command_queue, 'image_to_grid_rows'):
                 _lib.call('kib_image_to_grid_rows', layer.ptr, layer.padded_shape[1], size, n,
                           (image.ptr.value or 0) + pol * image_plane, image.padded_shape[2],
                           kernel1d.ptr, float(op.lm_scale), float(op.lm_bias), float(op.w),
-                          factors, 0 if factors is None else (1 if pol == 0 else 2), dtype, stream)
+                          factors, mode, dtype, stream)
             with profile_device(self.command_queue, 'image_to_grid_columns'):
                 _lib.call('kib_image_to_grid_columns',
                           (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,

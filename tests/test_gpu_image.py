@@ -452,3 +452,39 @@ def test_apply_primary_beam(gpu):
     fn()
     out = fn.buffer('data').get(queue)
     assert np.all(np.isnan(out[:, beam < 0.2])) and not np.any(np.isnan(out[:, beam >= 0.2]))
+
+
+def test_image_to_grid_sparse_model_rows(gpu, oracle):
+    """All-zero image rows are answered without a transform (sparse_model, the CLEAN-model
+    case): same grid as the dense route, also when the planes are occupied differently
+    (one of them not at all) and for a -0.0 / NaN-free image."""
+    context, queue = gpu
+    rs = RandomState(41)
+    pixels, grid_size, pols = 2048, 1230, 3
+    lm_scale = 0.2 / pixels
+    lm_bias = -lm_scale * pixels / 2
+    template = image.GridImageTemplate(context, np.float32)
+    plan = template.make_fft_plan((pixels, pixels), (pixels, pixels))
+    i2g = template.instantiate_image_to_grid(queue, (pols, grid_size, grid_size),
+                                             lm_scale, lm_bias, plan)
+    i2g.ensure_all_bound()
+    model = np.zeros((pols, pixels, pixels), np.float32)
+    model[0, rs.randint(0, pixels, 40), rs.randint(0, pixels, 40)] = rs.uniform(0.5, 2.0, 40)
+    model[2, rs.randint(0, pixels, 7), rs.randint(0, pixels, 7)] = rs.uniform(-2.0, -0.5, 7)
+    model[2, 5, :] = -0.0
+    kernel1d = rs.uniform(1.0, 2.0, pixels).astype(np.float32)
+    i2g.buffer('image').set(queue, model)
+    i2g.buffer('kernel1d').set(queue, kernel1d)
+    i2g.set_w(21.5)
+    results = []
+    for sparse in (True, False):
+        i2g.sparse_model = sparse
+        i2g.buffer('grid').set(queue, np.full((pols, grid_size, grid_size), 7 + 7j, np.complex64))
+        i2g()
+        results.append(i2g.buffer('grid').get(queue))
+    scale = np.abs(results[1]).max()
+    assert np.abs(results[0] - results[1]).max() <= 1e-6 * scale
+    assert not results[0][1].any()                      # the empty plane gives an exactly zero grid
+    expected = oracle.image_to_grid(model, kernel1d, lm_scale, lm_bias, np.float64(21.5),
+                                    grid_size=grid_size)
+    assert np.abs(results[0] - expected).max() / np.abs(expected).max() < 2e-5

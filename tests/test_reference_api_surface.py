@@ -53,27 +53,8 @@ def test_names_used_by_reference_operations_exist():
 
 
 def test_reference_imaging_template_constructs_over_this_package():
-    saved = {k: v for k, v in sys.modules.items()
-             if k == 'katsdpsigproc' or k.startswith('katsdpsigproc.') or k.startswith('katsdpimager.')
-             or k == 'katsdpimager'}
-    try:
-        sigproc = types.ModuleType('katsdpsigproc')
-        sigproc.__path__ = []
-        for name in ('accel', 'fft', 'fill', 'tune'):
-            module = importlib.import_module('katsdpimager_b200.' + name)
-            sys.modules['katsdpsigproc.' + name] = module
-            setattr(sigproc, name, module)
-        sys.modules['katsdpsigproc'] = sigproc
-        package = types.ModuleType('katsdpimager')
-        package.__path__ = [os.path.join(REFERENCE, 'katsdpimager')]
-        sys.modules['katsdpimager'] = package
-        for name in ('grid', 'image', 'clean', 'weight', 'predict', 'profiling'):
-            sys.modules['katsdpimager.' + name] = importlib.import_module('katsdpimager_b200.' + name)
-        spec = importlib.util.spec_from_file_location('katsdpimager.imaging', IMAGING)
-        ref_imaging = importlib.util.module_from_spec(spec)
-        sys.modules['katsdpimager.imaging'] = ref_imaging
-        spec.loader.exec_module(ref_imaging)
-
+    from tests import reference_loader
+    with reference_loader.reference_imaging() as ref_imaging:
         from katsdpimager_b200 import clean, parameters as prm, weight
         fixed_image = prm.FixedImageParameters([1, 2, 3, 4], np.float32)
         fixed_grid = prm.FixedGridParameters(7.0, 8, 4, 1000.0, 7, degrid=True)
@@ -85,8 +66,4 @@ def test_reference_imaging_template_constructs_over_this_package():
         assert template.degridder is not None and template.clean.num_polarizations == 4
         # the Imaging class of the reference subclasses our OperationSequence
         assert issubclass(ref_imaging.Imaging, sys.modules['katsdpsigproc.accel'].OperationSequence)
-    finally:
-        for key in [k for k in sys.modules if k == 'katsdpsigproc' or k.startswith('katsdpsigproc.')
-                    or k == 'katsdpimager' or k.startswith('katsdpimager.')]:
-            del sys.modules[key]
-        sys.modules.update(saved)
+    assert 'katsdpimager.imaging' not in sys.modules
