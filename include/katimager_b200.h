@@ -402,6 +402,27 @@ int kib_predict(void *vis, const int16_t *uv, const int16_t *w_plane, const floa
  * returns the flop count in *flops; the caller times it with events. */
 int kib_fp32_peak_kernel(float *sink, int blocks, int iters, double *flops, kib_stream_t stream);
 
+/* ---- visibility preprocessing
+ * kib_preprocess replaces visibility_collector<P>::add for ONE channel (reference
+ * katsdpimager/preprocess.cpp:401-513 add_impl2 + :335-397 compress; pybind11 entry point
+ * `_preprocess.VisibilityCollector.add`, preprocess.cpp:673): Mueller/Stokes transform with
+ * MulZ arithmetic, weight transform, w < 0 flip + conjugate, quantisation (subpixel_coord
+ * :313-323), flagged samples dropped, adjacent duplicates merged within each `capacity`-sample
+ * buffer (0 = one buffer), stable bucket sort by W slice.
+ *   uvw float[n][3] metres, weights float[n][Q], vis complex64[n][Q]           (device)
+ *   feed_angle1/2 float[n] or NULL; mueller_stokes complex64 [P][Q] (no feed angles) or
+ *   [P][4]; mueller_circular complex64 [4][Q] or NULL                            (device)
+ *   records: n x (12 + 12 P) bytes {int16 uv[2], sub_uv[2], w_plane, w_slice; float
+ *   weights[P]; complex64 vis[P]} in W-slice order (device); counts[w_slices]  (HOST, the
+ *   call synchronises the stream).  scratch: kib_preprocess_scratch_bytes. */
+int kib_preprocess_scratch_bytes(int64_t num_vis, int num_pols, int w_slices, int64_t *bytes);
+int kib_preprocess(const float *uvw, const float *weights, const void *vis, int64_t num_vis,
+                   int num_in_pols, const float *feed_angle1, const float *feed_angle2,
+                   const void *mueller_stokes, const void *mueller_circular, int num_pols,
+                   double cell_size, double max_w, int w_slices, int w_planes, int oversample,
+                   int64_t capacity, void *records, int64_t *host_counts,
+                   void *scratch, int64_t scratch_bytes, kib_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,9 @@ SIGNATURES = {
     'kib_fill': [_vp, _i, _i64, _i, _i, _i, _d, _i, _vp],
     'kib_unpack_records': [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp],
     'kib_predict': [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _f, _vp],
+    'kib_preprocess_scratch_bytes': [_i64, _i, _i, POINTER(c_int64)],
+    'kib_preprocess': [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _d, _d, _i, _i, _i, _i64,
+                       _vp, POINTER(c_int64), _vp, _i64, _vp],
     'kib_fp32_peak_kernel': [_vp, _i, _i, POINTER(c_double), _vp],
 }
 
@@ -171,6 +174,8 @@ def call(name, *args):
         kernel_launches += 2                 # column transforms + unfold
     elif name == 'kib_grid_to_image':
         kernel_launches += 1 + load().kib_grid_to_image_columns_kernels(int(args[8]))
+    elif name == 'kib_preprocess':
+        kernel_launches += 4                 # quantise, heads, merge, gather (+ cub scan / sort)
     elif name == 'kib_clean_minor_cycles':
         kernel_launches += load().kib_clean_minor_cycles_launches(int(args[26]), int(args[31]))
 

@@ -26,25 +26,91 @@ from .profiling import profile_device
 
 
 class ResidentVisibilities:
-    """Preprocessed visibility records of one channel, one device array per W slice.
+    """Preprocessed visibility records of one channel in HBM, W slices back to back.
 
     `slices` is a sequence of contiguous record arrays (fields ``uv, sub_uv, w_plane,
     weights, vis``; one entry per W slice, possibly empty).  Uploads are enqueued on
     `command_queue`; pinned arrays (:class:`~.accel.HostArray`) are copied without staging.
+    :meth:`from_raw` builds the same object from raw correlator output, preprocessed on the
+    device.
     """
 
     def __init__(self, command_queue, slices, num_polarizations):
         self.command_queue = command_queue
         self.num_polarizations = num_polarizations
         self.record_bytes = 12 + 12 * num_polarizations
-        self.counts = [len(s) for s in slices]
-        context = command_queue.context
-        self.device = [accel.DeviceArray(context, (n * self.record_bytes,), np.uint8) if n else None
-                       for n in self.counts]
+        self._set_counts([len(s) for s in slices])
+        self.buffer = accel.DeviceArray(command_queue.context,
+                                        (max(1, len(self)) * self.record_bytes,), np.uint8)
         self.h2d_bytes = 0
         self._keepalive = []
         self._uploaded = None
         self.upload(slices)
+
+    def _set_counts(self, counts):
+        self.counts = [int(c) for c in counts]
+        self.offsets = [int(o) * self.record_bytes
+                        for o in np.concatenate(([0], np.cumsum(self.counts)[:-1]))]
+
+    @classmethod
+    def from_raw(cls, command_queue, uvw, weights, vis, image_parameters, grid_parameters,
+                 mueller_stokes=None, feed_angle1=None, feed_angle2=None, mueller_circular=None,
+                 capacity=0):
+        """Preprocess one channel on the device (``kib_preprocess``: the whole of the
+        reference's ``VisibilityCollector.add``, preprocess.cpp:401-513 + :335-397).
+
+        uvw : (N, 3) float32 metres;  weights : (N, Q) float32;  vis : (N, Q) complex64, the
+        raw correlation products; `mueller_stokes` (P x Q, or P x 4 with feed angles) maps them
+        to the image's polarizations (identity by default).  The raw arrays are uploaded
+        once; the records are produced in HBM and never visit the host.
+        """
+        ip, gp = image_parameters, grid_parameters
+        P = len(ip.fixed.polarizations)
+        uvw = np.ascontiguousarray(uvw, np.float32)
+        weights = np.ascontiguousarray(weights, np.float32)
+        vis = np.ascontiguousarray(vis, np.complex64)
+        n, Q = vis.shape
+        if mueller_stokes is None:
+            if P != Q:
+                raise ValueError('mueller_stokes is required when P != Q')
+            mueller_stokes = np.identity(P, np.complex64)
+        context = command_queue.context
+        self = cls.__new__(cls)
+        self.command_queue = command_queue
+        self.num_polarizations = P
+        self.record_bytes = 12 + 12 * P
+        self.buffer = accel.DeviceArray(context, (max(1, n) * self.record_bytes,), np.uint8)
+        self._keepalive = []
+        self.h2d_bytes = 0
+
+        def upload(array):
+            if array is None:
+                return None
+            array = np.ascontiguousarray(array)
+            dev = accel.DeviceArray(context, array.shape, array.dtype)
+            dev.set(command_queue, array)
+            self.h2d_bytes += array.nbytes
+            return dev
+        inputs = [upload(a) for a in (
+            uvw, weights, vis,
+            None if feed_angle1 is None else np.asarray(feed_angle1, np.float32),
+            None if feed_angle2 is None else np.asarray(feed_angle2, np.float32),
+            np.asarray(mueller_stokes, np.complex64),
+            None if mueller_circular is None else np.asarray(mueller_circular, np.complex64))]
+        nbytes = _lib.c_int64()
+        _lib.call('kib_preprocess_scratch_bytes', n, P, gp.w_slices, _lib.ctypes.byref(nbytes))
+        scratch = accel.DeviceArray(context, (max(1, nbytes.value),), np.uint8)
+        counts = (_lib.c_int64 * gp.w_slices)()
+        with profile_device(command_queue, 'preprocess'):
+            _lib.call('kib_preprocess', *[d.ptr if d is not None else None for d in inputs[:3]],
+                      n, Q, *[d.ptr if d is not None else None for d in inputs[3:]], P,
+                      float(np.float32(ip.cell_size)), float(np.float32(gp.fixed.max_w)),
+                      gp.w_slices, gp.w_planes, gp.fixed.oversample, int(capacity),
+                      self.buffer.ptr, counts, scratch.ptr, scratch.shape[0],
+                      command_queue.stream)
+        self._set_counts(list(counts))
+        self._uploaded = command_queue.enqueue_marker()
+        return self
 
     def upload(self, slices):
         """(Re-)upload the records; `slices` must have the lengths given at construction."""
@@ -53,8 +119,9 @@ class ResidentVisibilities:
         queue = self.command_queue
         keepalive = []
         self.h2d_bytes = 0
-        for records, dev in zip(slices, self.device):
-            if dev is None:
+        base = self.buffer.ptr.value or 0
+        for records, offset in zip(slices, self.offsets):
+            if len(records) == 0:
                 continue
             if records.dtype.itemsize != self.record_bytes or not records.flags.c_contiguous:
                 raise TypeError('records must be contiguous {}-byte structures'.format(
@@ -65,7 +132,7 @@ class ResidentVisibilities:
                 pinned = accel.HostArray((nbytes,), np.uint8, context=queue.context)
                 pinned[:] = raw
                 raw = pinned
-            _lib.call('kib_memcpy_h2d_async', dev.ptr, raw.ctypes.data, nbytes, queue.stream)
+            _lib.call('kib_memcpy_h2d_async', base + offset, raw.ctypes.data, nbytes, queue.stream)
             keepalive.append(raw)
             self.h2d_bytes += nbytes
         if self._uploaded is not None and self._keepalive:
@@ -94,17 +161,31 @@ class ResidentVisibilities:
         for start in range(0, n, block_size):
             yield start, min(block_size, n - start)
 
+    def get(self, w_slice):
+        """Records of a W slice as a host record array (blocking; for tests)."""
+        from . import preprocess
+        n = self.counts[w_slice]
+        host = np.empty(n * self.record_bytes, np.uint8)
+        if n:
+            queue = self.command_queue
+            pinned = accel.HostArray(host.shape, np.uint8, context=queue.context)
+            _lib.call('kib_memcpy_d2h_async', pinned.ctypes.data,
+                      (self.buffer.ptr.value or 0) + self.offsets[w_slice], host.nbytes,
+                      queue.stream)
+            queue.finish()
+            host[:] = pinned
+        return host.view(preprocess.make_dtype(self.num_polarizations)).view(np.recarray)
+
     def unpack(self, queue, w_slice, start, count, uv=None, w_plane=None, weights=None,
                vis=None, vis_from_weights=False):
         """Split records [start, start + count) of a slice into per-field device buffers."""
         def ptr(buffer):
             return buffer.ptr if buffer is not None else None
-        base = (self.device[w_slice].ptr.value or 0) + start * self.record_bytes
+        base = (self.buffer.ptr.value or 0) + self.offsets[w_slice] + start * self.record_bytes
         with profile_device(queue, 'unpack_records'):
             _lib.call('kib_unpack_records', base, self.record_bytes, count,
                       self.num_polarizations, ptr(uv), ptr(w_plane), ptr(weights), ptr(vis),
                       int(vis_from_weights), queue.stream)
-
 
     def feed(self, imager, w_slice, start, count, field, with_weights):
         """Make records [start, start + count) the imager's current chunk."""

@@ -67,6 +67,11 @@ def quantise(uvw, weights, vis, image_parameters, grid_parameters):
 
 def compress(records, w_slice):
     """Merge adjacent records with identical coordinates (preprocess.cpp:335-373)."""
+    # elements whose first weight is zero are flagged (a NaN visibility squashed by quantise)
+    # and skipped before runs are detected (preprocess.cpp:341-352)
+    keep = records.weights[:, 0] != 0
+    if not np.all(keep):
+        records, w_slice = records[keep].view(np.recarray), w_slice[keep]
     if len(records) == 0:
         return records, w_slice
     key = np.empty((len(records), 6), np.int16)

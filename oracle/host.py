@@ -408,3 +408,39 @@ def predict(vis, uv, sub_uv, w_plane, weights, lmn, flux, oversample, uv_scale, 
                       ctypes.c_float(oversample), ctypes.c_float(uv_scale),
                       ctypes.c_float(w_scale), ctypes.c_float(w_bias))
     return vis
+
+
+# --------------------------------------------------------------------------------------
+# Preprocessing (preprocess.cpp:313-513)
+def preprocess_dtype(num_polarizations):
+    """vis_t<P> including the w_slice field (preprocess.cpp:39-52)."""
+    P = num_polarizations
+    return np.dtype([('uv', 'i2', (2,)), ('sub_uv', 'i2', (2,)), ('w_plane', 'i2'),
+                     ('w_slice', 'i2'), ('weights', 'f4', (P,)), ('vis', 'c8', (P,))])
+
+
+def preprocess(uvw, weights, vis, mueller_stokes, num_polarizations, cell_size, max_w, w_slices,
+               w_planes, oversample, feed_angle1=None, feed_angle2=None, mueller_circular=None,
+               capacity=0):
+    """visibility_collector<P>::add for one channel (see oracle.c kor_preprocess).  Returns
+    (records ordered by W slice, counts per slice)."""
+    uvw = _c(uvw, np.float32)
+    weights = _c(weights, np.float32)
+    vis = _c(vis, np.complex64)
+    n, Q = vis.shape
+    P = num_polarizations
+    stokes = _c(mueller_stokes, np.complex64)
+    circular = _c(mueller_circular, np.complex64) if mueller_circular is not None else None
+    f1 = _c(feed_angle1, np.float32) if feed_angle1 is not None else None
+    f2 = _c(feed_angle2, np.float32) if feed_angle2 is not None else None
+    assert stokes.shape == ((P, Q) if f1 is None else (P, 4))
+    out = np.zeros(max(n, 1), preprocess_dtype(P))
+    counts = np.zeros(w_slices, np.int64)
+    fn = lib().kor_preprocess
+    fn.restype = ctypes.c_long
+    total = fn(_ptr(uvw), _ptr(weights), _ptr(vis), ctypes.c_long(n), Q,
+               _ptr(f1) if f1 is not None else None, _ptr(f2) if f2 is not None else None,
+               _ptr(stokes), _ptr(circular) if circular is not None else None, P,
+               ctypes.c_float(cell_size), ctypes.c_float(max_w), w_slices, w_planes, oversample,
+               ctypes.c_long(capacity), _ptr(out), _ptr(counts))
+    return out[:total].view(np.recarray), counts

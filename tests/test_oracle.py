@@ -230,3 +230,85 @@ def test_grid_to_image_threaded_matches(oracle):
         oracle.grid_to_image_threaded(grid[0], actual, taper, lm_scale, lm_bias,
                                       np.float64(31.5), pool, 3)
     assert np.abs(actual - expected[0]).max() <= 1e-6 * np.abs(expected).max()
+
+
+def _reference_preprocess_case():
+    """Inputs and expected records of the reference's own preprocessing test
+    (reference katsdpimager/test/test_preprocess.py:76-136)."""
+    uvw = np.array([[12.1, 2.3, 4.7], [12.102, 2.299, 4.6], [-5.2, -10.6, 7.2],
+                    [-1.0, 2.0, 3.0]], np.float32)
+    weights = np.array([
+        [[1.3, 0.6, 1.2, 0.1], [1.1, 1.2, 1.3, 1.4], [0.5, 0.6, 0.7, 0.8], [1.0, 0.0, 1.0, 1.0]],
+        [[0.2, 2.4, 1.2, 2.6], [2.8, 2.6, 2.4, 2.2], [1.6, 1.4, 1.2, 1.0], [2.0, 2.0, 0.0, 2.0]]],
+        np.float32)
+    vis = np.array([
+        [[0.5 - 2.3j, 0.1 + 4.2j, 0.0 - 3j, 1.5 + 0j], [1.2 + 3.4j, 5.6 + 7.8j, 9.0 + 1.2j, 3.4 + 5.6j],
+         [1.5 + 1.3j, 1.1 + 2.7j, 1.0 - 2j, 2.5 + 1j], [10.0, 10.0, 10.0, 10.0]],
+        [[3.0 + 0j, 0.0 - 6j, 0.2 + 8.4j, 1.0 - 4.6j], [6.8 + 11.2j, 18.0 + 2.4j, 11.2 + 15.6j, 2.4 + 6.8j],
+         [3.0 + 2j, 2.0 - 4j, 2.2 + 5.4j, 3.0 + 2.6j], [20.0, 20.0, 20.0, 20.0]]], np.complex64)
+    expected = [
+        dict(uv=[[96, 18], [-42, -85]], sub_uv=[[6, 3], [3, 1]], w_plane=[64, 65],
+             weights=[[2.4, 1.8, 2.5, 1.5], [0.5, 0.6, 0.7, 0.8]],
+             vis=[[1.97 + 0.75j, 6.78 + 11.88j, 11.7 - 2.04j, 4.91 + 7.84j],
+                  [0.75 + 0.65j, 0.66 + 1.62j, 0.7 - 1.4j, 2.0 + 0.8j]]),
+        dict(uv=[[387, 73], [387, 73], [-167, -340]], sub_uv=[[1, 4], [2, 4], [4, 6]],
+             w_plane=[64, 64, 65],
+             weights=[[0.2, 2.4, 1.2, 2.6], [2.8, 2.6, 2.4, 2.2], [1.6, 1.4, 1.2, 1.0]],
+             vis=[[0.6 + 0.0j, 0.0 - 14.4j, 0.24 + 10.08j, 2.6 - 11.96j],
+                  [19.04 + 31.36j, 46.8 + 6.24j, 26.88 + 37.44j, 5.28 + 14.96j],
+                  [4.8 + 3.2j, 2.8 - 5.6j, 2.64 + 6.48j, 3.0 + 2.6j]])]
+    # cell sizes of the test's two channels: wavelength / (pixel_size * pixels), pixel_size =
+    # 1 / (4096 wavelength), pixels = 2048 -> 2 wavelength^2 ... in metres: 0.125, 0.03125
+    cells = [0.25 / ((1.0 / (4096.0 * 0.25)) * 2048), 0.125 / ((1.0 / (4096.0 * 0.125)) * 2048)]
+    return uvw, weights, vis, expected, cells
+
+
+@pytest.mark.parametrize('feed_angles', [False, True])
+def test_preprocess_reference_records(oracle, feed_angles):
+    """oracle.preprocess (restatement of preprocess.cpp) against the reference's expected
+    records, with the static Mueller matrix and through the parallactic-angle generator
+    (zero feed angles, identity matrices, as the reference tests it)."""
+    uvw, weights, vis, expected, cells = _reference_preprocess_case()
+    identity = np.identity(4, np.complex64)
+    for channel in range(2):
+        kwargs = dict(feed_angle1=np.zeros(4, np.float32), feed_angle2=np.zeros(4, np.float32),
+                      mueller_circular=identity) if feed_angles else {}
+        records, counts = oracle.preprocess(uvw, weights[channel], vis[channel], identity, 4,
+                                            cells[channel], 400.0, 1, 128, 8, capacity=64,
+                                            **kwargs)
+        want = expected[channel]
+        assert list(counts) == [len(want['uv'])]
+        np.testing.assert_array_equal(records.uv, want['uv'])
+        np.testing.assert_array_equal(records.sub_uv, want['sub_uv'])
+        np.testing.assert_array_equal(records.w_plane, want['w_plane'])
+        np.testing.assert_allclose(records.weights, want['weights'])
+        np.testing.assert_allclose(records.vis, want['vis'], rtol=1e-5)
+
+
+def test_preprocess_matches_numpy_port(oracle):
+    """...and against the numpy producer used by the benchmarks (identity Mueller matrix),
+    on a random set with flagged samples, NaNs, negative w, several W slices and merging."""
+    from katsdpimager_b200 import parameters as prm, preprocess
+    rs = np.random.RandomState(5)
+    n = 5000
+    uvw = (rs.standard_normal((n, 3)) * [300.0, 300.0, 150.0]).astype(np.float32)
+    uvw[100:140] = uvw[100]                    # a run of duplicates
+    weights = rs.uniform(0.5, 1.5, (n, 2)).astype(np.float32)
+    weights[rs.randint(0, n, 200), rs.randint(0, 2, 200)] = 0.0
+    vis = (rs.standard_normal((n, 2)) + 1j * rs.standard_normal((n, 2))).astype(np.complex64)
+    vis[rs.randint(0, n, 50), 0] = np.nan
+    fixed = prm.FixedImageParameters([1, 2], np.float32)
+    ip = prm.ImageParameters(fixed, wavelength=0.2, pixels=2048, pixel_size=0.0001)
+    gp = prm.GridParameters(prm.FixedGridParameters(7.0, 8, 4, 600.0, 7), 5, 16)
+    records, counts = oracle.preprocess(uvw, weights, vis, np.identity(2, np.complex64), 2,
+                                        np.float32(ip.cell_size), 600.0, 5, 16, 8)
+    q, w_slice = preprocess.quantise(uvw, weights, vis, ip, gp)
+    q, w_slice = preprocess.compress(q, w_slice)
+    slices = preprocess.bucket_by_slice(q, w_slice, 5)
+    assert list(counts) == [len(s) for s in slices]
+    expected = np.concatenate(slices).view(np.recarray)
+    np.testing.assert_array_equal(records.uv, expected.uv)
+    np.testing.assert_array_equal(records.sub_uv, expected.sub_uv)
+    np.testing.assert_array_equal(records.w_plane, expected.w_plane)
+    np.testing.assert_allclose(records.weights, expected.weights, rtol=3e-7)
+    np.testing.assert_allclose(records.vis, expected.vis, rtol=1e-6, atol=1e-6)
