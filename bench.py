@@ -58,8 +58,8 @@ UNIT = 'vis/s'
 #: CLEAN work of the step as the B200 run of this synthetic channel executes it (CLEAN is bit
 #: exact, so the host path would run the same cycles): PSF patch side and minor cycles over the
 #: MAJOR major cycles.  Only used to size the CPU sample; the GPU arm reports what it ran.
-NOMINAL_PATCH = 1501
-NOMINAL_MINOR = 300
+NOMINAL_PATCH = 1145
+NOMINAL_MINOR = 541
 
 
 def make_parameters(channel):
@@ -437,7 +437,7 @@ def _resident(queue, slices):
 
 
 def run_gpu(args, ranks):
-    from katsdpimager_b200 import _lib, accel, imaging, io, pipeline, profiling, weight
+    from katsdpimager_b200 import _lib, accel, beam, imaging, io, pipeline, profiling, weight
 
     context = accel.Context(ranks.local_rank)
     queue = context.create_command_queue()
@@ -461,8 +461,11 @@ def run_gpu(args, ranks):
     resident = _resident(queue, pinned_slices)
     resident.wait()
 
+    restorer = beam.Restorer(context)
+
     def step_resident():
-        return pipeline.process_channel(imager, resident, ip, gp, cp, wp, MAJOR, VIS_BLOCK)
+        return pipeline.process_channel(imager, resident, ip, gp, cp, wp, MAJOR, VIS_BLOCK,
+                                        restore=restorer)
 
     # ---- FP32 roofline denominator: FFMA micro-benchmark on all SMs
     sink = accel.DeviceArray(context, (1,), np.float32)
@@ -528,7 +531,8 @@ def run_gpu(args, ranks):
 
     def step_e2e():
         e2e_vis.upload(pinned_slices)
-        pipeline.process_channel(imager, e2e_vis, ip, gp, cp, wp, MAJOR, VIS_BLOCK)
+        pipeline.process_channel(imager, e2e_vis, ip, gp, cp, wp, MAJOR, VIS_BLOCK,
+                                 restore=restorer)
         cube.store_device(ranks.rank, imager.buffer('dirty'), queue)
 
     step_e2e()

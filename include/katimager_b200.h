@@ -100,6 +100,13 @@ int kib_memcpy3d_async(void *dst, size_t dst_row_pitch, size_t dst_plane_pitch,
  * unnormalised, in place allowed). ny x nx complex elements, contiguous rows
  * of `row_stride` elements (row_stride == nx unless padded). */
 int kib_fft_plan2d_create(kib_fft_plan_t *plan, int ny, int nx, int row_stride, int dtype);
+/* Real <-> half-complex 2-D plans (katsdpsigproc.fft.FftTemplate with a real source or
+ * destination, beam.py:327-330): ny x nx real rows of real_row_stride elements, ny x (nx/2+1)
+ * complex rows of complex_row_stride elements; inverse = 0 real -> complex, 1 complex -> real
+ * (unnormalised; the input of the inverse is overwritten).  Executed with
+ * kib_fft_plan2d_exec (direction ignored). */
+int kib_fft_plan2d_real_create(kib_fft_plan_t *plan, int ny, int nx, int real_row_stride,
+                               int complex_row_stride, int inverse, int dtype);
 int kib_fft_plan2d_exec(kib_fft_plan_t plan, void *src, void *dst, int direction,
                         kib_stream_t stream);
 int kib_fft_plan2d_destroy(kib_fft_plan_t plan);
@@ -362,6 +369,11 @@ int kib_mean_weight(const float *grid, int row_stride, int width, int height,
  * (device double[3]). */
 int kib_density_weights(float *grid, int row_stride, int64_t pol_stride, int width, int height,
                         int num_pols, float a, float b, double *sums, kib_stream_t stream);
+/* kib_fourier_beam replaces FourierBeam._run (beam.py:271-301) + fourier_beam.mako: the
+ * half-complex transform of an image times amplitude * exp(a v^2 + b u v + c u^2), u = column,
+ * v = signed row frequency (restoring-beam convolution). */
+int kib_fourier_beam(void *data, int row_stride, double amplitude, double a, double b, double c,
+                     int width, int height, int dtype, kib_stream_t stream);
 /* kib_fits_plane writes an image in the order the reference's FITS writer stores it
  * (io.py:186-200: l axis reversed, big-endian, rows packed): out[p][y][x] =
  * byteswap(image[p][y][width-1-x]).  float32 only. */

@@ -51,6 +51,7 @@ SIGNATURES = {
     'kib_memcpy_d2d_async': [_vp, _vp, _sz, _vp],
     'kib_memcpy3d_async': [_vp, _sz, _sz, _vp, _sz, _sz, _sz, _sz, _sz, _i, _vp],
     'kib_fft_plan2d_create': [POINTER(c_void_p), _i, _i, _i, _i],
+    'kib_fft_plan2d_real_create': [POINTER(c_void_p), _i, _i, _i, _i, _i, _i],
     'kib_fft_plan1d_create': [POINTER(c_void_p), _i, _i64, _i64, _i, _i],
     'kib_fft_plan2d_exec': [_vp, _vp, _vp, _i, _vp],
     'kib_fft_plan2d_destroy': [_vp],
@@ -99,6 +100,7 @@ SIGNATURES = {
     'kib_grid_weights': [_vp, _i, _i64, _i, _i, _vp, _vp, _i, _i64, _vp],
     'kib_mean_weight': [_vp, _i, _i, _i, _vp, _vp],
     'kib_density_weights': [_vp, _i, _i64, _i, _i, _i, _f, _f, _vp, _vp],
+    'kib_fourier_beam': [_vp, _i, _d, _d, _d, _d, _i, _i, _i, _vp],
     'kib_fits_plane': [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp],
     'kib_fill': [_vp, _i, _i64, _i, _i, _i, _d, _i, _vp],
     'kib_unpack_records': [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp],
@@ -154,7 +156,7 @@ _ONE_KERNEL = frozenset([
     'kib_image_to_layer', 'kib_scale', 'kib_add_image', 'kib_apply_primary_beam',
     'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
     'kib_abs_histogram', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
-    'kib_density_weights', 'kib_fill', 'kib_fits_plane', 'kib_predict', 'kib_fp32_peak_kernel',
+    'kib_density_weights', 'kib_fill', 'kib_fits_plane', 'kib_fourier_beam', 'kib_predict', 'kib_fp32_peak_kernel',
     'kib_unpack_records', 'kib_grid_to_image_rows', 'kib_image_to_grid_rows'])
 
 #: number of hand-written kernels launched through this module (cuFFT and memset/memcpy

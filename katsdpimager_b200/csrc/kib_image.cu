@@ -324,6 +324,27 @@ fits_plane_kernel(unsigned *__restrict__ out, const unsigned *__restrict__ image
         out[p * (long long) width * height + o] = __byte_perm(image[p * pol_stride + in], 0, 0x0123);
 }
 
+// Fourier transform of the image (real-to-complex layout: height x (width / 2 + 1)) times the
+// analytic transform of the Gaussian restoring beam, amplitude * exp(a v^2 + b u v + c u^2)
+// with v the signed row frequency and u the column frequency (beam.py:271-301,
+// fourier_beam.mako).
+template <typename Real>
+__global__ void __launch_bounds__(256)
+fourier_beam_kernel(typename Complex2<Real>::type *__restrict__ data, int stride, Real amplitude,
+                    Real a, Real b, Real c, int width, int height)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= width) return;
+    const Real u = (Real) x;
+    const Real v = (Real) (2 * y >= height ? y - height : y);
+    const Real ft = amplitude * exp((a * v + b * u) * v + c * u * u);
+    typename Complex2<Real>::type value = data[(long long) y * stride + x];
+    value.x *= ft;
+    value.y *= ft;
+    data[(long long) y * stride + x] = value;
+}
+
 static dim3 row_grid(int width, int height) { return dim3(divup(width, 256), height, 1); }
 
 }  // namespace kib
@@ -505,6 +526,23 @@ int kib_apply_primary_beam(void *image, int row_stride, int64_t pol_stride,
             static_cast<double *>(image), row_stride, pol_stride,
             static_cast<const double *>(beam_power), width, height, num_pols,
             threshold, replacement);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_fourier_beam(void *data, int row_stride, double amplitude, double a, double b, double c,
+                     int width, int height, int dtype, kib_stream_t stream)
+{
+    KIB_CHECK_DTYPE("kib_fourier_beam");
+    if (width <= 0 || height <= 0) return 0;
+    dim3 g = row_grid(width, height);
+    if (dtype == KIB_F32)
+        fourier_beam_kernel<float><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<float2 *>(data), row_stride, (float) amplitude, (float) a, (float) b,
+            (float) c, width, height);
+    else
+        fourier_beam_kernel<double><<<g, 256, 0, as_stream(stream)>>>(
+            static_cast<double2 *>(data), row_stride, amplitude, a, b, c, width, height);
     KIB_CHECK_LAUNCH();
     return 0;
 }

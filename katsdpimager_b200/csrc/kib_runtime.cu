@@ -35,6 +35,7 @@ int sm_count()
 struct FftPlan {
     cufftHandle handle;
     int dtype;
+    int kind = 0;       // 0 complex <-> complex, 1 real -> complex, 2 complex -> real
 };
 
 static const char *cufft_error_string(cufftResult r)
@@ -331,6 +332,46 @@ int kib_fft_plan2d_create(kib_fft_plan_t *plan, int ny, int nx, int row_stride, 
     return 0;
 }
 
+int kib_fft_plan2d_real_create(kib_fft_plan_t *plan, int ny, int nx, int real_row_stride,
+                               int complex_row_stride, int inverse, int dtype)
+{
+    KIB_REQUIRE(plan != nullptr, "kib_fft_plan2d_real_create: null argument");
+    KIB_REQUIRE(ny > 0 && nx > 0 && real_row_stride >= nx && complex_row_stride >= nx / 2 + 1,
+                "kib_fft_plan2d_real_create: bad shape");
+    KIB_REQUIRE(dtype == KIB_F32 || dtype == KIB_F64, "kib_fft_plan2d_real_create: bad dtype");
+    FftPlan *p = new FftPlan;
+    p->dtype = dtype;
+    p->kind = inverse ? 2 : 1;
+    cufftResult r = cufftCreate(&p->handle);
+    if (r != CUFFT_SUCCESS) {
+        delete p;
+        set_error("cufftCreate failed: %s", cufft_error_string(r));
+        return 1000 + (int) r;
+    }
+    long long n[2] = {ny, nx};
+    long long real_embed[2] = {ny, real_row_stride};
+    long long complex_embed[2] = {ny, complex_row_stride};
+    size_t work_size = 0;
+    cufftType type = dtype == KIB_F32 ? (inverse ? CUFFT_C2R : CUFFT_R2C)
+                                      : (inverse ? CUFFT_Z2D : CUFFT_D2Z);
+    if (inverse)
+        r = cufftMakePlanMany64(p->handle, 2, n, complex_embed, 1,
+                                (long long) ny * complex_row_stride, real_embed, 1,
+                                (long long) ny * real_row_stride, type, 1, &work_size);
+    else
+        r = cufftMakePlanMany64(p->handle, 2, n, real_embed, 1,
+                                (long long) ny * real_row_stride, complex_embed, 1,
+                                (long long) ny * complex_row_stride, type, 1, &work_size);
+    if (r != CUFFT_SUCCESS) {
+        cufftDestroy(p->handle);
+        delete p;
+        set_error("cufftMakePlanMany64(real %d x %d) failed: %s", ny, nx, cufft_error_string(r));
+        return 1000 + (int) r;
+    }
+    *plan = reinterpret_cast<kib_fft_plan_t>(p);
+    return 0;
+}
+
 int kib_fft_plan1d_create(kib_fft_plan_t *plan, int n, int64_t stride, int64_t dist,
                           int batch, int dtype)
 {
@@ -367,6 +408,24 @@ int kib_fft_plan2d_exec(kib_fft_plan_t plan, void *src, void *dst, int direction
     FftPlan *p = reinterpret_cast<FftPlan *>(plan);
     int dir = direction == KIB_FFT_FORWARD ? CUFFT_FORWARD : CUFFT_INVERSE;
     KIB_CUFFT(cufftSetStream(p->handle, as_stream(stream)));
+    if (p->kind == 1) {
+        if (p->dtype == KIB_F32)
+            KIB_CUFFT(cufftExecR2C(p->handle, static_cast<cufftReal *>(src),
+                                   static_cast<cufftComplex *>(dst)));
+        else
+            KIB_CUFFT(cufftExecD2Z(p->handle, static_cast<cufftDoubleReal *>(src),
+                                   static_cast<cufftDoubleComplex *>(dst)));
+        return 0;
+    }
+    if (p->kind == 2) {
+        if (p->dtype == KIB_F32)
+            KIB_CUFFT(cufftExecC2R(p->handle, static_cast<cufftComplex *>(src),
+                                   static_cast<cufftReal *>(dst)));
+        else
+            KIB_CUFFT(cufftExecZ2D(p->handle, static_cast<cufftDoubleComplex *>(src),
+                                   static_cast<cufftDoubleReal *>(dst)));
+        return 0;
+    }
     if (p->dtype == KIB_F32)
         KIB_CUFFT(cufftExecC2C(p->handle, static_cast<cufftComplex *>(src),
                                static_cast<cufftComplex *>(dst), dir));
