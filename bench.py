@@ -605,7 +605,7 @@ def run_gpu(args, ranks):
                 'avg_launch_ms': secs / count * 1e3, 'ms_per_step': secs / args.steps * 1e3}
 
     rows_roofline = hbm_roofline(
-        'grid_to_image_rows', 'rows_kernel<8192,256,16,16,2> (kib_gridfft.cu)',
+        'grid_to_image_rows', 'rows_kernel<8192,512,16,16,2> (kib_gridfft.cu)',
         8.0 * N * G + 8.0 * N * N, 'fused_rows_dram_bytes_per_launch',
         'algorithmic bytes = 8 N G (half-transformed plane) + 8 N^2 (image read + write)')
     rooflines = {
