@@ -538,10 +538,22 @@ def run_gpu(args, ranks):
     step_e2e()
     queue.finish()
     ranks.barrier()
+    profiler = None
+    if os.environ.get('KIB_BENCH_DEBUG'):
+        import cProfile
+        profiler = cProfile.Profile()
+        profiler.enable()
     t0 = queue.enqueue_marker()
     for _ in range(args.steps):
+        h0 = time.monotonic()
         step_e2e()
+        if profiler is not None:
+            print('e2e step host ms', (time.monotonic() - h0) * 1e3, file=sys.stderr, flush=True)
     t1 = queue.enqueue_marker()
+    if profiler is not None:
+        import pstats
+        profiler.disable()
+        pstats.Stats(profiler, stream=sys.stderr).sort_stats('cumulative').print_stats(25)
     t1.wait()
     queue.finish()
     e2e_seconds = ranks.max(t1.time_since(t0)) / args.steps

@@ -244,12 +244,14 @@ class ConvolveBeam(accel.OperationSequence):
         self._fourier_beam.beam = value
 
 
-def extract_psf(queue, psf, psf_patch):
+def extract_psf(queue, psf, psf_patch, out=None):
     """Central `psf_patch` = (rows, cols) of polarization 0 of a device PSF on the host
-    (reference frontend.extract_psf, frontend.py:152-173)."""
+    (reference frontend.extract_psf, frontend.py:152-173); `out` may supply the pinned
+    destination."""
     y0 = (psf.shape[1] - psf_patch[0]) // 2
     x0 = (psf.shape[2] - psf_patch[1]) // 2
-    out = accel.HostArray((psf_patch[0], psf_patch[1]), psf.dtype, context=queue.context)
+    if out is None:
+        out = accel.HostArray((psf_patch[0], psf_patch[1]), psf.dtype, context=queue.context)
     psf.get_region(queue, out, np.s_[0, y0:y0 + psf_patch[0], x0:x0 + psf_patch[1]], np.s_[:, :])
     return out
 
@@ -263,16 +265,24 @@ class Restorer:
     def __init__(self, context):
         self.context = context
         self._op = None
+        self._shape = None
+        self._core = None
         self.beam = None
 
     def __call__(self, imager, psf_patch):
         queue = imager.command_queue
         model = imager.buffer('model')
-        self.beam = fit_beam(extract_psf(queue, imager.buffer('psf'), psf_patch[1:]))
-        if self._op is None or self._op.template.shape != tuple(model.shape[1:]):
-            template = ConvolveBeamTemplate(self.context, model.shape[1:], model.dtype)
+        psf = imager.buffer('psf')
+        core_shape = (int(psf_patch[1]), int(psf_patch[2]))
+        if self._core is None or self._core.shape != core_shape or self._core.dtype != psf.dtype:
+            self._core = accel.HostArray(core_shape, psf.dtype, context=queue.context)
+        self.beam = fit_beam(extract_psf(queue, psf, core_shape, self._core))
+        shape = tuple(model.shape[1:])
+        if self._op is None or self._shape != shape or self._op.command_queue is not queue:
+            template = ConvolveBeamTemplate(self.context, shape, model.dtype)
             self._op = template.instantiate(queue)
             self._op.ensure_all_bound()
+            self._shape = shape
         self._op.beam = self.beam
         plane = self._op.buffer('image')
         for pol in range(model.shape[0]):

@@ -18,6 +18,7 @@ inline cudaStream_t as_stream(kib_stream_t s) { return reinterpret_cast<cudaStre
         if (kib_err__ != cudaSuccess) {                                             \
             ::kib::set_error("%s failed: %s (%s:%d)", #expr,                        \
                              cudaGetErrorString(kib_err__), __FILE__, __LINE__);    \
+            (void) cudaGetLastError();   /* reported here: do not leave it for a later launch check */ \
             return (int) kib_err__;                                                 \
         }                                                                           \
     } while (0)

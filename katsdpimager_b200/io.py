@@ -205,7 +205,9 @@ class FitsCube:
         self.data = np.memmap(filename, dtype='>f4', mode=mode, offset=self.header_size,
                               shape=self.shape)
         self._pinned = None
+        self._bounce = False
         self._staging = None
+        self._host = None
 
     @classmethod
     def create(cls, filename, num_channels, image_parameters, first_frequency_hz,
@@ -237,8 +239,14 @@ class FitsCube:
         plane_bytes = int(np.prod(self.shape[1:])) * 4
         start = self.data.ctypes.data + first_channel * plane_bytes
         nbytes = (last_channel - first_channel) * plane_bytes
-        _lib.call('kib_host_register', start, nbytes)
-        self._pinned = start
+        try:
+            _lib.call('kib_host_register', start, nbytes)
+            self._pinned = start
+        except _lib.KibError:
+            # the driver refuses to page-lock some file mappings (e.g. files on an overlay or
+            # network file system; tmpfs works): fall back to a pinned bounce buffer
+            self._pinned = None
+            self._bounce = True
 
     def unpin(self):
         if self._pinned is not None:
@@ -260,8 +268,16 @@ class FitsCube:
         _lib.call('kib_fits_plane', self._staging.ptr, image.ptr, image.padded_shape[2],
                   image.padded_shape[1] * image.padded_shape[2], width, height, pols,
                   _lib.dtype_code(image.dtype), queue.stream)
-        _lib.call('kib_memcpy_d2h_async', self.data[channel].ctypes.data, self._staging.ptr,
-                  nbytes, queue.stream)
+        if self._pinned is not None:
+            _lib.call('kib_memcpy_d2h_async', self.data[channel].ctypes.data, self._staging.ptr,
+                      nbytes, queue.stream)
+        else:
+            if self._host is None or self._host.shape[0] < nbytes:
+                self._host = accel.HostArray((nbytes,), np.uint8, context=queue.context)
+            _lib.call('kib_memcpy_d2h_async', self._host.ctypes.data, self._staging.ptr,
+                      nbytes, queue.stream)
+            queue.finish()
+            self.data[channel].view(np.uint8).reshape(-1)[:] = self._host[:nbytes]
 
     def flush(self):
         self.data.flush()

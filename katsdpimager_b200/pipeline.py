@@ -294,7 +294,12 @@ def process_channel(imager, vis, image_parameters, grid_parameters, clean_parame
     make_dirty(imager, vis, 'weights', mid_w, vis_block, degrid)
     stats['passes'] += 1
     dirty = imager.buffer('dirty')
-    psf_peak = accel.HostArray((dirty.shape[0],), dirty.dtype, context=queue.context)
+    # pinned scratch is kept on the imager: freeing page-locked memory synchronises the device
+    # and costs ~0.1 s once large mappings are registered (profiles/e2e_diag2.py)
+    psf_peak = getattr(imager, '_psf_peak_host', None)
+    if psf_peak is None or psf_peak.shape != (dirty.shape[0],) or psf_peak.dtype != dirty.dtype:
+        psf_peak = accel.HostArray((dirty.shape[0],), dirty.dtype, context=queue.context)
+        imager._psf_peak_host = psf_peak
     dirty.get_region(queue, psf_peak,
                      np.s_[:, dirty.shape[1] // 2, dirty.shape[2] // 2], np.s_[:])
     if np.any(psf_peak == 0):
