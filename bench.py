@@ -436,13 +436,96 @@ def _resident(queue, slices):
     return pipeline.ResidentVisibilities(queue, slices, POLS)
 
 
+def side_rows(context, queue, hbm_peak, fp32_peak):
+    """Rows of SURVEY.md section 8 that the channel job does not exercise at their own BASELINE
+    configuration: direct prediction (config 3: 1000 sources) and the CLEAN minor cycle
+    (config 5: 4096^2, 1000 cycles), each timed with events on a few repetitions."""
+    import types
+    from katsdpimager_b200 import accel, clean, predict
+    rows = {}
+    # ---- predict, config 3: 2^20 visibilities x 1000 sources x 4 polarizations
+    fixed = prm.FixedImageParameters([1, 2, 3, 4], np.float32)
+    array = prm.ArrayParameters(simulate.DISH_DIAMETER, simulate.longest_baseline())
+    ip3 = prm.ImageParameters(fixed, wavelength=0.2155, pixels=4096, array=array)
+    gp3 = prm.GridParameters(prm.FixedGridParameters(7.0, OVERSAMPLE, 4, array.longest_baseline,
+                                                     KERNEL_WIDTH), W_SLICES, W_PLANES)
+    nvis, nsrc = 1 << 20, 1000
+    op = predict.PredictTemplate(context, np.float32, POLS).instantiate(queue, ip3, gp3, nvis, nsrc)
+    op.ensure_all_bound()
+    rs = np.random.RandomState(3)
+    lmn, flux = simulate.random_sources(nsrc, 0.4 * ip3.pixels * ip3.pixel_size, POLS)
+    op.set_sources(lmn, flux)
+    uv = np.stack([rs.randint(-1200, 1200, nvis), rs.randint(-1200, 1200, nvis),
+                   rs.randint(0, OVERSAMPLE, nvis), rs.randint(0, OVERSAMPLE, nvis)], axis=1)
+    op.buffer('uv').set(queue, uv.astype(np.int16))
+    op.buffer('w_plane').set(queue, rs.randint(0, W_PLANES, nvis).astype(np.int16))
+    op.buffer('weights').set(queue, rs.uniform(0.5, 1.5, (nvis, POLS)).astype(np.float32))
+    op.buffer('vis').zero(queue)
+    op.num_vis = nvis
+    op.set_w(100.0)
+    for _ in range(2):
+        op()
+    queue.finish()
+    a = queue.enqueue_marker()
+    for _ in range(5):
+        op()
+    b = queue.enqueue_marker()
+    b.wait()
+    seconds = b.time_since(a) / 5
+    pairs = float(nvis) * nsrc
+    flops = pairs * (5 + 8 * POLS + 16)       # phase 5, complex MAC per pol, ~16 for the sincos
+    rows['predict'] = {
+        'config': 'BASELINE configs[2]: 2^20 visibilities x 1000 sources x 4 polarizations',
+        'kernel': 'predict_kernel (kib_predict.cu)', 'ms': seconds * 1e3,
+        'vis_sources_per_sec': pairs / seconds, 'bound': 'fp32 + sfu',
+        'achieved': flops / seconds / 1e12, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
+        'frac': flops / seconds / fp32_peak,
+        'note': 'flops per (visibility, source): 5 for the phase, 8 P for the complex '
+                'multiply-accumulates, the polynomial sincos counted as 16'}
+    # ---- CLEAN, config 5: 4096^2, 1000 minor cycles
+    from tests.test_gpu_baseline_shapes import _clean_inputs
+    for pols, mode, side in ((1, clean.CLEAN_I, 255), (4, clean.CLEAN_SUMSQ, 255),
+                             (4, clean.CLEAN_SUMSQ, 1023)):
+        dirty, psf = _clean_inputs(4096, pols, 40 + pols)
+        fx = prm.FixedImageParameters([1, 2, 3, 4][:pols], np.float32)
+        ipc = types.SimpleNamespace(fixed=fx, pixels=4096)
+        cpc = prm.CleanParameters(1000, 0.1, 0.85, 5.0, mode, 0.01, 0.5, 0.02)
+        cl = clean.CleanTemplate(context, cpc, np.float32, pols).instantiate(queue, ipc)
+        cl.ensure_all_bound()
+        cl.buffer('dirty').set(queue, dirty)
+        cl.buffer('psf').set(queue, psf)
+        cl.buffer('model').zero(queue)
+        cl.reset()
+        patch = (pols, side, side)
+        cl.run_cycles(patch, 0.0, 50)
+        queue.finish()
+        a = queue.enqueue_marker()
+        components, _ = cl.run_cycles(patch, 0.0, 1000)
+        b = queue.enqueue_marker()
+        b.wait()
+        seconds = b.time_since(a)
+        nbytes = 12.0 * side * side * pols
+        gbs = nbytes * len(components) / seconds / 1e9
+        rows['clean_{}pol_{}'.format(pols, side)] = {
+            'config': 'BASELINE configs[4]: 4096^2, {} pol, {}^2 patch, 1000 minor cycles in one '
+                      'launch'.format(pols, side),
+            'kernel': 'clean_persistent_kernel (kib_clean.cu)', 'cycles': len(components),
+            'cycles_per_sec': len(components) / seconds,
+            'us_per_cycle': seconds / len(components) * 1e6, 'bound': 'hbm (L2-resident patch)',
+            'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak}
+        del cl
+    return rows
+
+
 def run_gpu(args, ranks):
     from katsdpimager_b200 import _lib, accel, beam, imaging, io, pipeline, profiling, weight
 
     context = accel.Context(ranks.local_rank)
     queue = context.create_command_queue()
-    channel = ranks.rank * (NUM_CHANNELS // max(ranks.world, 1)) % NUM_CHANNELS
-    array, ip, gp, slices = make_channel(channel, args.dumps)
+    # weak scaling with FIXED work per GPU: every rank images its own copy of channel 0 (other
+    # channels of the band differ in PSF patch size and CLEAN depth, which would measure the
+    # slowest channel instead of the scaling; profiles/r02_scaling.md has such a run too)
+    array, ip, gp, slices = make_channel(0, args.dumps)
     work = step_work(slices)
     total_vis = work['vis']
     mid_w = prm.slice_mid_w(ip, gp)
@@ -538,22 +621,10 @@ def run_gpu(args, ranks):
     step_e2e()
     queue.finish()
     ranks.barrier()
-    profiler = None
-    if os.environ.get('KIB_BENCH_DEBUG'):
-        import cProfile
-        profiler = cProfile.Profile()
-        profiler.enable()
     t0 = queue.enqueue_marker()
     for _ in range(args.steps):
-        h0 = time.monotonic()
         step_e2e()
-        if profiler is not None:
-            print('e2e step host ms', (time.monotonic() - h0) * 1e3, file=sys.stderr, flush=True)
     t1 = queue.enqueue_marker()
-    if profiler is not None:
-        import pstats
-        profiler.disable()
-        pstats.Stats(profiler, stream=sys.stderr).sort_stats('cumulative').print_stats(25)
     t1.wait()
     queue.finish()
     e2e_seconds = ranks.max(t1.time_since(t0)) / args.steps
@@ -640,6 +711,21 @@ def run_gpu(args, ranks):
             'degrid', 'degrid_kernel (kib_degrid.cu)', work['degridded_vis'],
             'degrid_dram_bytes_per_vis', 10 + 20 * POLS),
     }
+    cells = float(grid_size) ** 2
+    rooflines['grid_weights'] = hbm_roofline(
+        'grid_weights', 'grid_weights_kernel (kib_weight.cu)',
+        (8.0 + 8.0 * POLS) * min(VIS_BLOCK, total_vis), None,
+        'per visibility: uv 8 B + weights 4 P B read, 4 P B of atomic adds (W1, robust weights); '
+        'bytes for a full 1 Mi-visibility chunk')
+    rooflines['density_weights'] = hbm_roofline(
+        'density_weights', 'density_weights_kernel (kib_weight.cu)', 8.0 * POLS * cells, None,
+        '8 P B per grid cell (read + write)')
+    rooflines['noise_est'] = hbm_roofline(
+        'abs_histogram', 'abs_histogram_kernel (kib_clean.cu): one radix digit of the exact median',
+        4.0 * POLS * (PIXELS - 2 * round(cp.border * PIXELS)) ** 2, None,
+        '4 B per pixel inside the border per pass; 3 passes per estimate')
+    rooflines['scale'] = hbm_roofline(
+        'scale', 'scale_kernel (kib_image.cu)', 8.0 * POLS * N * N, None, '8 B per pixel')
     clean_count, clean_secs = per_kernel.get('clean_cycles', (0, 0.0))
     patch = stats.get('psf_patch_size', (0, 0))
     if clean_count and stats.get('minor'):
@@ -656,6 +742,9 @@ def run_gpu(args, ranks):
             'note': '12 B per patch pixel and polarization (psf read, dirty read + write); the '
                     'patch is L2-resident between cycles, the cycle is a chain of dependent '
                     'L2 round trips (DESIGN.md section 4.4)'}
+    extra_rows = {}
+    if ranks.world == 1:
+        extra_rows = side_rows(context, queue, hbm_peak, fp32_peak)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ranks.world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_seconds * 1e3,
@@ -675,6 +764,7 @@ def run_gpu(args, ranks):
         'work_per_step': work,
         'roofline': rows_roofline,
         'rooflines': {k: v for k, v in rooflines.items() if v is not None},
+        'rows': extra_rows,
         'kernels_ms_per_step': {k: v[1] / args.steps * 1e3 for k, v in sorted(per_kernel.items())},
         'parity': parity,
     }

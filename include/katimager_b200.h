@@ -346,6 +346,15 @@ int kib_abs_histogram(const void *image, int row_stride, int64_t pol_stride,
                       int width, int height, int num_pols, int border,
                       uint32_t prefix, int prefix_bits, int shift, int bits,
                       uint32_t *hist, int dtype, kib_stream_t stream);
+/* kib_abs_histogram_window: digit (shift, bits) of |pixel| inside the border for the three
+ * adjacent leading prefixes first_prefix .. first_prefix + 2 (hist[3][1 << bits]) and the count
+ * of values whose prefix is smaller (*below): the first two radix passes of the exact median
+ * in one when the leading digit can be guessed (NoiseEst, clean.py:247-353). */
+int kib_abs_histogram_window(const void *image, int row_stride, int64_t pol_stride,
+                             int width, int height, int num_pols, int border,
+                             uint32_t first_prefix, int prefix_bits, int shift, int bits,
+                             uint32_t *hist, unsigned long long *below, int dtype,
+                             kib_stream_t stream);
 /* The reference's own kernel, kept for API parity (rank.mako): number of
  * |pixels| strictly below `value` inside the border, accumulated into
  * rank (device uint64[1], zeroed by the caller). */

@@ -96,6 +96,8 @@ SIGNATURES = {
     'kib_clean_minor_cycles_launches': [_i, _i],
     'kib_psf_patch': [_vp, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _i, _vp],
     'kib_abs_histogram': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _vp, _i, _vp],
+    'kib_abs_histogram_window': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _vp, _vp, _i,
+                                 _vp],
     'kib_rank': [_vp, _i, _i64, _i, _i, _i, _i, _d, _vp, _i, _vp],
     'kib_grid_weights': [_vp, _i, _i64, _i, _i, _vp, _vp, _i, _i64, _vp],
     'kib_mean_weight': [_vp, _i, _i, _i, _vp, _vp],
@@ -155,7 +157,7 @@ _ONE_KERNEL = frozenset([
     'kib_grid', 'kib_degrid', 'kib_grid_to_layer', 'kib_layer_to_grid', 'kib_layer_to_image',
     'kib_image_to_layer', 'kib_scale', 'kib_add_image', 'kib_apply_primary_beam',
     'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
-    'kib_abs_histogram', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
+    'kib_abs_histogram', 'kib_abs_histogram_window', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
     'kib_density_weights', 'kib_fill', 'kib_fits_plane', 'kib_fourier_beam', 'kib_predict', 'kib_fp32_peak_kernel',
     'kib_unpack_records', 'kib_grid_to_image_rows', 'kib_image_to_grid_rows'])
 
@@ -173,7 +175,7 @@ def call(name, *args):
     elif name == 'kib_grid_to_image_columns':
         kernel_launches += load().kib_grid_to_image_columns_kernels(int(args[2]))
     elif name == 'kib_image_to_grid_columns':
-        kernel_launches += 2                 # column transforms + unfold
+        kernel_launches += load().kib_grid_to_image_columns_kernels(int(args[5]))
     elif name == 'kib_grid_to_image':
         kernel_launches += 1 + load().kib_grid_to_image_columns_kernels(int(args[8]))
     elif name == 'kib_preprocess':

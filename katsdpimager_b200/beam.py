@@ -257,26 +257,43 @@ def extract_psf(queue, psf, psf_patch, out=None):
 
 
 class Restorer:
-    """The restore step of ``frontend.process_channel`` (frontend.py:529-531, 623-636) as a
-    callable for :func:`~.pipeline.process_channel`: fits the beam to the PSF core, convolves
-    every polarization of the model with it.  One scratch plane and one half-complex plane
-    are allocated on first use and kept."""
+    """The restore step of ``frontend.process_channel`` for :func:`~.pipeline.process_channel`:
+    ``extract`` copies the PSF core to the host right after the PSF patch is known (where the
+    reference fits the beam, frontend.py:529-531), ``fit`` runs the host-side Gaussian fit --
+    the pipeline calls it after enqueuing the first dirty pass, so the ~10 ms fit hides behind
+    device work -- and calling the object convolves every polarization of the model with the
+    beam (frontend.py:623-636).  One scratch plane, one half-complex plane and the pinned core
+    buffer are allocated on first use and kept."""
 
     def __init__(self, context):
         self.context = context
         self._op = None
         self._shape = None
         self._core = None
+        self._pending = False
         self.beam = None
 
-    def __call__(self, imager, psf_patch):
+    def extract(self, imager, psf_patch):
         queue = imager.command_queue
-        model = imager.buffer('model')
         psf = imager.buffer('psf')
         core_shape = (int(psf_patch[1]), int(psf_patch[2]))
         if self._core is None or self._core.shape != core_shape or self._core.dtype != psf.dtype:
             self._core = accel.HostArray(core_shape, psf.dtype, context=queue.context)
-        self.beam = fit_beam(extract_psf(queue, psf, core_shape, self._core))
+        extract_psf(queue, psf, core_shape, self._core)
+        self._pending = True
+
+    def fit(self):
+        if self._pending:
+            self.beam = fit_beam(self._core)
+            self._pending = False
+        return self.beam
+
+    def __call__(self, imager, psf_patch):
+        queue = imager.command_queue
+        model = imager.buffer('model')
+        if self.beam is None and not self._pending:
+            self.extract(imager, psf_patch)
+        self.fit()
         shape = tuple(model.shape[1:])
         if self._op is None or self._shape != shape or self._op.command_queue is not queue:
             template = ConvolveBeamTemplate(self.context, shape, model.dtype)
@@ -289,4 +306,6 @@ class Restorer:
             model.copy_region(queue, plane, np.s_[pol], ())
             self._op()
             plane.copy_region(queue, model, (), np.s_[pol])
-        return self.beam
+        beam, self.beam = self.beam, None        # the next channel has its own PSF
+        self.last_beam = beam
+        return beam

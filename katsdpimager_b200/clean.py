@@ -160,8 +160,12 @@ class NoiseEst(accel.Operation):
         self.slots['dirty'] = accel.IOSlot([
             accel.Dimension(template.num_polarizations, exact=True),
             image_shape[1], image_shape[2]], template.dtype)
-        self.slots['rank'] = accel.IOSlot([accel.Dimension(2048, exact=True)], np.uint32)
-        self._hist_host = accel.HostArray((2048,), np.uint32, context=command_queue.context)
+        self.slots['rank'] = accel.IOSlot([accel.Dimension(3 * 2048 + 2, exact=True)], np.uint32)
+        self._hist_host = accel.HostArray((3 * 2048 + 2,), np.uint32,
+                                          context=command_queue.context)
+        #: leading radix digit of the last median: the next estimate of a similar image starts
+        #: from it and saves the (expensive) first pass
+        self._guess = None
 
     def _run(self):
         raise NotImplementedError('use __call__()')
@@ -179,9 +183,55 @@ class NoiseEst(accel.Operation):
         hist.get(self.command_queue, self._hist_host)
         return self._hist_host[:1 << bits].astype(np.int64)
 
+    def _select_from_guess(self, ranks):
+        """Order statistics when all of them have a leading digit within one of the guess: one
+        windowed pass (second digit for three adjacent leading digits + count below) and the
+        last pass; None if the guess was wrong."""
+        (shift0, bits0), (shift1, bits1) = self._DIGITS[0], self._DIGITS[1]
+        first = max(self._guess - 1, 0)
+        dirty = self.buffer('dirty')
+        hist = self.buffer('rank')
+        hist.zero(self.command_queue)
+        row_stride, pol_stride = _strides(dirty)
+        below_ptr = (hist.ptr.value or 0) + 3 * 2048 * 4
+        with profile_device(self.command_queue, 'abs_histogram'):
+            _lib.call('kib_abs_histogram_window', dirty.ptr, row_stride, pol_stride,
+                      dirty.shape[2], dirty.shape[1], dirty.shape[0], self.border_pixels,
+                      first, bits0, shift1, bits1, hist.ptr, below_ptr,
+                      _lib.dtype_code(dirty.dtype), self.command_queue.stream)
+        hist.get(self.command_queue, self._hist_host)
+        window = self._hist_host[:3 * 2048].astype(np.int64).reshape(3, 2048)
+        below = int(self._hist_host[3 * 2048:].view(np.uint64)[0])
+        flat = window.reshape(-1)
+        cumulative = np.cumsum(flat)
+        results = {}
+        for r in ranks:
+            local = r - below
+            if local < 0 or local >= cumulative[-1]:
+                return None
+        groups = {}
+        for r in ranks:
+            idx = int(np.searchsorted(cumulative, r - below, side='right'))
+            groups.setdefault(idx, []).append(r)
+        for idx, rs in groups.items():
+            prefix = ((first + idx // 2048) << bits1) | (idx % 2048)
+            offset = below + (int(cumulative[idx - 1]) if idx > 0 else 0)
+            shift2, bits2 = self._DIGITS[2]
+            last = self._histogram(prefix, 32 - shift2 - bits2, shift2, bits2)
+            cum2 = np.cumsum(last)
+            for r in rs:
+                bucket = int(np.searchsorted(cum2, r - offset, side='right'))
+                results[r] = (prefix << bits2) | bucket
+        return [np.array(results[r], np.uint32).view(np.float32) for r in ranks]
+
     def _select(self, ranks):
         """Exact order statistics (0-based `ranks`, ascending) of |dirty| inside the
         border, as float32 bit patterns, by most-significant-digit radix selection."""
+        if self._guess is not None:
+            found = self._select_from_guess(ranks)
+            if found is not None:
+                self._guess = int(found[-1].view(np.uint32)) >> self._DIGITS[0][0]
+                return found
         results = {}
         pending = [(0, 0, 0, list(ranks))]      # (pass index, prefix, rank offset, ranks)
         while pending:
@@ -202,6 +252,7 @@ class NoiseEst(accel.Operation):
                         results[r] = new_prefix
                 else:
                     pending.append((level + 1, new_prefix, offset + below, rs))
+        self._guess = results[ranks[-1]] >> self._DIGITS[0][0]
         return [np.array(results[r], np.uint32).view(np.float32) for r in ranks]
 
     def _binary_search(self):

@@ -717,6 +717,47 @@ abs_histogram_kernel(const float *__restrict__ image, int row_stride, long long 
         if (local[i] != 0) atomicAdd(&hist[i], local[i]);
 }
 
+// Second radix digit (bits shift .. shift+bits) of |pixel| for THREE adjacent values of the
+// leading digit (first_prefix, +1, +2) at once, plus the number of values whose leading digit
+// is smaller.  With a guess of the leading digit of the median (the previous estimate of the
+// same image is almost always within one bucket) this replaces the expensive first pass: the
+// second digit is spread evenly over its bins, so the shared-memory atomics do not collide.
+__global__ void __launch_bounds__(256)
+abs_histogram_window_kernel(const float *__restrict__ image, int row_stride, long long pol_stride,
+                            int inner_w, int inner_h, int P, int border,
+                            unsigned first_prefix, int prefix_shift, int shift, unsigned mask,
+                            unsigned *__restrict__ hist /* [3][mask + 1] */,
+                            unsigned long long *__restrict__ below)
+{
+    extern __shared__ unsigned local[];
+    const unsigned bins = mask + 1;
+    for (unsigned i = threadIdx.x; i < 3 * bins; i += blockDim.x) local[i] = 0;
+    __syncthreads();
+    const int rows = inner_h * P;
+    unsigned count_below = 0;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int p = r / inner_h, y = r - p * inner_h;
+        const float *row = image + p * pol_stride + (long long) (y + border) * row_stride + border;
+#pragma unroll 4
+        for (int x = threadIdx.x; x < inner_w; x += 256) {
+            const unsigned bits = __float_as_uint(fabsf(__ldg(row + x)));
+            const unsigned rel = (bits >> prefix_shift) - first_prefix;     // wraps when smaller
+            if (rel < 3u)
+                atomicAdd(&local[rel * bins + ((bits >> shift) & mask)], 1u);
+            else
+                count_below += (bits >> prefix_shift) < first_prefix;
+        }
+    }
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1)
+        count_below += __shfl_xor_sync(0xffffffffu, count_below, offset);
+    if ((threadIdx.x & 31) == 0 && count_below != 0)
+        atomicAdd(below, (unsigned long long) count_below);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < 3 * bins; i += blockDim.x)
+        if (local[i] != 0) atomicAdd(&hist[i], local[i]);
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(256)
 rank_kernel(const Real *__restrict__ image, int row_stride, long long pol_stride,
@@ -1046,6 +1087,32 @@ int kib_abs_histogram(const void *image, int row_stride, int64_t pol_stride,
     abs_histogram_kernel<<<blocks, 256, (mask + 1) * sizeof(unsigned), as_stream(stream)>>>(
         static_cast<const float *>(image), row_stride, pol_stride, inner_w, inner_h, num_pols,
         border, prefix, shift + bits, prefix_bits > 0, shift, mask, hist);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
+int kib_abs_histogram_window(const void *image, int row_stride, int64_t pol_stride,
+                             int width, int height, int num_pols, int border,
+                             uint32_t first_prefix, int prefix_bits, int shift, int bits,
+                             uint32_t *hist, unsigned long long *below, int dtype,
+                             kib_stream_t stream)
+{
+    KIB_REQUIRE(dtype == KIB_F32, "kib_abs_histogram_window: only float32 images are supported");
+    KIB_REQUIRE(bits >= 1 && bits <= 11 && shift >= 0 && prefix_bits >= 1
+                && prefix_bits + shift + bits == 32,
+                "kib_abs_histogram_window: bad digits (prefix %d, shift %d, bits %d)",
+                prefix_bits, shift, bits);
+    KIB_REQUIRE(hist != nullptr && below != nullptr, "kib_abs_histogram_window: null output");
+    const int inner_w = width - 2 * border, inner_h = height - 2 * border;
+    if (inner_w <= 0 || inner_h <= 0) return 0;
+    const unsigned mask = (1u << bits) - 1;
+    const long long rows = (long long) inner_h * num_pols;
+    int blocks = sm_count() * 8;
+    if (blocks > rows) blocks = (int) rows;
+    abs_histogram_window_kernel<<<blocks, 256, 3 * (mask + 1) * sizeof(unsigned),
+                                  as_stream(stream)>>>(
+        static_cast<const float *>(image), row_stride, pol_stride, inner_w, inner_h, num_pols,
+        border, first_prefix, shift + bits, shift, mask, hist, below);
     KIB_CHECK_LAUNCH();
     return 0;
 }

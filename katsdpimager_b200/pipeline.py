@@ -310,6 +310,8 @@ def process_channel(imager, vis, image_parameters, grid_parameters, clean_parame
     imager.dirty_to_psf()
     psf_patch = imager.psf_patch()
     stats['psf_patch_size'] = (psf_patch[2], psf_patch[1])
+    if restore is not None and hasattr(restore, 'extract'):
+        restore.extract(imager, psf_patch)      # PSF core to the host (frontend.py:529-531)
 
     # major cycles (frontend.py:549-585)
     stats['major'] = 0
@@ -318,6 +320,8 @@ def process_channel(imager, vis, image_parameters, grid_parameters, clean_parame
     for i in range(major):
         make_dirty(imager, vis, 'vis', mid_w, vis_block, degrid, full_cycle=i != 0)
         stats['passes'] += 1
+        if i == 0 and restore is not None and hasattr(restore, 'fit'):
+            restore.fit()                       # host-side beam fit while the device grids
         imager.scale_dirty(scale)
         stats['major'] += 1
         noise = imager.noise_est()

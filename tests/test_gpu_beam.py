@@ -64,7 +64,7 @@ def test_restore_in_pipeline(gpu):
         pipeline.process_channel(imager, vis, ip, gp, cp, wp, 2, fx['vis_block'], restore=restorer)
         outs.append((imager.get_buffer('dirty'), imager.get_buffer('model')))
     (plain, model), (restored, restored_model) = outs
-    b = restorer.beam
+    b = restorer.last_beam
     assert 1.5 < b.minor <= b.major < 20
     expected_model = beam.convolve_beam(model.astype(np.float64), b)
     np.testing.assert_allclose(restored_model, expected_model, rtol=0,

@@ -356,3 +356,27 @@ def test_clean_large_patch(gpu, oracle):
         value, pos, pixel = host(patch, 0.0)
         assert tuple(record['pos']) == pos and record['value'] == value
     np.testing.assert_array_equal(fn.buffer('dirty').get(queue), host_dirty)
+
+
+def test_noise_est_guessed_leading_digit(gpu, oracle):
+    """Repeated estimates start from the leading radix digit of the previous median (one
+    windowed pass instead of two): still the exact median, whether the guess is right (same
+    or slightly scaled image), off by one bucket, or wrong (image scaled by 50: full select)."""
+    context, queue = gpu
+    rs = np.random.RandomState(8)
+    pols, n = 2, 1024
+    base = (rs.standard_normal((pols, n, n)) * 3e-3).astype(np.float32)
+    base[0, 100:200, 100:300] += 0.5
+    fn = clean.NoiseEstTemplate(context, np.float32, pols).instantiate(queue, (pols, n, n), 0.03)
+    fn.ensure_all_bound()
+    for scale in (1.0, 1.0, 1.02, 1.25, 0.7, 50.0, 50.0, 1e-3):
+        image = (base * np.float32(scale)).astype(np.float32)
+        fn.buffer('dirty').set(queue, image)
+        assert fn() == oracle.noise_est(image, 0.03), scale
+    # odd number of pixels: a single middle element
+    fn = clean.NoiseEstTemplate(context, np.float32, 1).instantiate(queue, (1, 301, 301), 0.01)
+    fn.ensure_all_bound()
+    image = rs.standard_normal((1, 301, 301)).astype(np.float32)
+    for _ in range(2):
+        fn.buffer('dirty').set(queue, image)
+        assert fn() == oracle.noise_est(image, 0.01)
