@@ -238,6 +238,22 @@ int kib_image_to_grid_rows(void *scratch, int scratch_row_stride, int grid_size,
 int kib_image_to_grid_columns(void *grid_plane, int grid_row_stride, int grid_size,
                               const void *scratch, int scratch_row_stride, int size,
                               void *fold_scratch, int dtype, kib_stream_t stream);
+/* Image -> grid of a SPARSE image (a CLEAN model: zero except for a few hundred pixels; the
+ * result is identical to the dense route for any image).  kib_image_to_grid_rows_sparse finds
+ * the rows of the plane that hold a non-zero pixel (row_info: int32[2 * size + 1], owned by the
+ * caller: [0] count, [1 .. size] layer rows, [size + 1 ..] one flag per layer row), transforms
+ * only those (factor computed on the fly) and leaves the other rows of `scratch` untouched;
+ * kib_image_to_grid_columns_sparse takes rows flagged empty as zero without reading them.
+ * Available where the column pass is the single cluster kernel
+ * (kib_image_to_grid_sparse_supported). */
+int kib_image_to_grid_sparse_supported(int size, int grid_size, int dtype);
+int kib_image_to_grid_rows_sparse(void *scratch, int scratch_row_stride, int grid_size, int size,
+                                  const void *image_plane, int image_row_stride,
+                                  const void *kernel1d, double lm_scale, double lm_bias, double w,
+                                  int32_t *row_info, int dtype, kib_stream_t stream);
+int kib_image_to_grid_columns_sparse(void *grid_plane, int grid_row_stride, int grid_size,
+                                     const void *scratch, int scratch_row_stride, int size,
+                                     const int32_t *row_info, int dtype, kib_stream_t stream);
 
 /* kib_image_to_layer replaces image_to_layer.mako (oracle image.py:836-843):
  *   layer[ifftshift(y,x)] = image[y][x] / (kernel1d[y]*kernel1d[x]*n) * exp(-2 pi i w (n-1)) */
@@ -346,14 +362,14 @@ int kib_abs_histogram(const void *image, int row_stride, int64_t pol_stride,
                       int width, int height, int num_pols, int border,
                       uint32_t prefix, int prefix_bits, int shift, int bits,
                       uint32_t *hist, int dtype, kib_stream_t stream);
-/* kib_abs_histogram_window: digit (shift, bits) of |pixel| inside the border for the three
- * adjacent leading prefixes first_prefix .. first_prefix + 2 (hist[3][1 << bits]) and the count
- * of values whose prefix is smaller (*below): the first two radix passes of the exact median
- * in one when the leading digit can be guessed (NoiseEst, clean.py:247-353). */
+/* kib_abs_histogram_window: digit (shift, bits) of |pixel| inside the border for `window`
+ * adjacent leading prefixes first_prefix ... (hist[window][1 << bits], at most 8192 bins in all)
+ * and the count of values whose prefix is smaller (*below): the first two radix passes of the
+ * exact median in one when the leading digit can be guessed (NoiseEst, clean.py:247-353). */
 int kib_abs_histogram_window(const void *image, int row_stride, int64_t pol_stride,
                              int width, int height, int num_pols, int border,
-                             uint32_t first_prefix, int prefix_bits, int shift, int bits,
-                             uint32_t *hist, unsigned long long *below, int dtype,
+                             uint32_t first_prefix, int window, int prefix_bits, int shift,
+                             int bits, uint32_t *hist, unsigned long long *below, int dtype,
                              kib_stream_t stream);
 /* The reference's own kernel, kept for API parity (rank.mako): number of
  * |pixels| strictly below `value` inside the border, accumulated into

@@ -77,6 +77,9 @@ SIGNATURES = {
     'kib_grid_to_image_columns_kernels': [_i],
     'kib_image_to_grid_rows': [_vp, _i, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
     'kib_image_to_grid_columns': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
+    'kib_image_to_grid_sparse_supported': [_i, _i, _i],
+    'kib_image_to_grid_rows_sparse': [_vp, _i, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _vp],
+    'kib_image_to_grid_columns_sparse': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
     'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
     'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
@@ -96,8 +99,8 @@ SIGNATURES = {
     'kib_clean_minor_cycles_launches': [_i, _i],
     'kib_psf_patch': [_vp, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _i, _vp],
     'kib_abs_histogram': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _vp, _i, _vp],
-    'kib_abs_histogram_window': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _vp, _vp, _i,
-                                 _vp],
+    'kib_abs_histogram_window': [_vp, _i, _i64, _i, _i, _i, _i, c_uint32, _i, _i, _i, _i, _vp, _vp,
+                                 _i, _vp],
     'kib_rank': [_vp, _i, _i64, _i, _i, _i, _i, _d, _vp, _i, _vp],
     'kib_grid_weights': [_vp, _i, _i64, _i, _i, _vp, _vp, _i, _i64, _vp],
     'kib_mean_weight': [_vp, _i, _i, _i, _vp, _vp],
@@ -176,6 +179,10 @@ def call(name, *args):
         kernel_launches += load().kib_grid_to_image_columns_kernels(int(args[2]))
     elif name == 'kib_image_to_grid_columns':
         kernel_launches += load().kib_grid_to_image_columns_kernels(int(args[5]))
+    elif name == 'kib_image_to_grid_rows_sparse':
+        kernel_launches += 2                 # row classification + transforms of non-empty rows
+    elif name == 'kib_image_to_grid_columns_sparse':
+        kernel_launches += 1
     elif name == 'kib_grid_to_image':
         kernel_launches += 1 + load().kib_grid_to_image_columns_kernels(int(args[8]))
     elif name == 'kib_preprocess':

@@ -147,7 +147,9 @@ class NoiseEst(accel.Operation):
     **rank** : uint32[2048] histogram scratch
     """
 
-    _DIGITS = ((21, 11), (10, 11), (0, 10))     # (shift, bits) of the three radix passes
+    #: (shift, bits) of the three radix passes: sign + exponent, 10 and 13 mantissa bits
+    _DIGITS = ((23, 9), (13, 10), (0, 13))
+    _WINDOW = 8                 # leading digits covered by a guessed pass (a factor of 256)
 
     def __init__(self, template, command_queue, image_shape, border, allocator=None):
         if image_shape[0] != template.num_polarizations:
@@ -160,8 +162,8 @@ class NoiseEst(accel.Operation):
         self.slots['dirty'] = accel.IOSlot([
             accel.Dimension(template.num_polarizations, exact=True),
             image_shape[1], image_shape[2]], template.dtype)
-        self.slots['rank'] = accel.IOSlot([accel.Dimension(3 * 2048 + 2, exact=True)], np.uint32)
-        self._hist_host = accel.HostArray((3 * 2048 + 2,), np.uint32,
+        self.slots['rank'] = accel.IOSlot([accel.Dimension(8192 + 2, exact=True)], np.uint32)
+        self._hist_host = accel.HostArray((8192 + 2,), np.uint32,
                                           context=command_queue.context)
         #: leading radix digit of the last median: the next estimate of a similar image starts
         #: from it and saves the (expensive) first pass
@@ -176,47 +178,54 @@ class NoiseEst(accel.Operation):
         hist.zero(self.command_queue)
         row_stride, pol_stride = _strides(dirty)
         with profile_device(self.command_queue, 'abs_histogram'):
-            _lib.call('kib_abs_histogram', dirty.ptr, row_stride, pol_stride,
-                      dirty.shape[2], dirty.shape[1], dirty.shape[0], self.border_pixels,
-                      prefix, prefix_bits, shift, bits, hist.ptr,
-                      _lib.dtype_code(dirty.dtype), self.command_queue.stream)
+            if prefix_bits > 0:
+                # few values match a prefix: plain shared-memory atomics, no warp aggregation
+                _lib.call('kib_abs_histogram_window', dirty.ptr, row_stride, pol_stride,
+                          dirty.shape[2], dirty.shape[1], dirty.shape[0], self.border_pixels,
+                          prefix, 1, prefix_bits, shift, bits, hist.ptr,
+                          (hist.ptr.value or 0) + 8192 * 4,
+                          _lib.dtype_code(dirty.dtype), self.command_queue.stream)
+            else:
+                _lib.call('kib_abs_histogram', dirty.ptr, row_stride, pol_stride,
+                          dirty.shape[2], dirty.shape[1], dirty.shape[0], self.border_pixels,
+                          prefix, prefix_bits, shift, bits, hist.ptr,
+                          _lib.dtype_code(dirty.dtype), self.command_queue.stream)
         hist.get(self.command_queue, self._hist_host)
         return self._hist_host[:1 << bits].astype(np.int64)
 
     def _select_from_guess(self, ranks):
-        """Order statistics when all of them have a leading digit within one of the guess: one
-        windowed pass (second digit for three adjacent leading digits + count below) and the
-        last pass; None if the guess was wrong."""
-        (shift0, bits0), (shift1, bits1) = self._DIGITS[0], self._DIGITS[1]
-        first = max(self._guess - 1, 0)
+        """Order statistics when all of them have a leading digit (exponent) within a factor of
+        16 of the guess: one windowed pass (second digit for _WINDOW adjacent leading digits +
+        count below) and the last pass; None if the guess was too far off."""
+        (shift0, bits0), (shift1, bits1), (shift2, bits2) = self._DIGITS
+        bins = 1 << bits1
+        window = self._WINDOW
+        first = min(max(self._guess - window // 2, 0), (1 << bits0) - window)
         dirty = self.buffer('dirty')
         hist = self.buffer('rank')
         hist.zero(self.command_queue)
         row_stride, pol_stride = _strides(dirty)
-        below_ptr = (hist.ptr.value or 0) + 3 * 2048 * 4
+        below_ptr = (hist.ptr.value or 0) + 8192 * 4
         with profile_device(self.command_queue, 'abs_histogram'):
             _lib.call('kib_abs_histogram_window', dirty.ptr, row_stride, pol_stride,
                       dirty.shape[2], dirty.shape[1], dirty.shape[0], self.border_pixels,
-                      first, bits0, shift1, bits1, hist.ptr, below_ptr,
+                      first, window, bits0, shift1, bits1, hist.ptr, below_ptr,
                       _lib.dtype_code(dirty.dtype), self.command_queue.stream)
         hist.get(self.command_queue, self._hist_host)
-        window = self._hist_host[:3 * 2048].astype(np.int64).reshape(3, 2048)
-        below = int(self._hist_host[3 * 2048:].view(np.uint64)[0])
-        flat = window.reshape(-1)
+        flat = self._hist_host[:window * bins].astype(np.int64)
+        below = int(self._hist_host[8192:].view(np.uint64)[0])
         cumulative = np.cumsum(flat)
-        results = {}
         for r in ranks:
-            local = r - below
-            if local < 0 or local >= cumulative[-1]:
+            if r - below < 0 or r - below >= cumulative[-1]:
                 return None
         groups = {}
         for r in ranks:
             idx = int(np.searchsorted(cumulative, r - below, side='right'))
             groups.setdefault(idx, []).append(r)
+        results = {}
         for idx, rs in groups.items():
-            prefix = ((first + idx // 2048) << bits1) | (idx % 2048)
+            prefix = ((first + idx // bins) << bits1) | (idx % bins)
             offset = below + (int(cumulative[idx - 1]) if idx > 0 else 0)
-            shift2, bits2 = self._DIGITS[2]
             last = self._histogram(prefix, 32 - shift2 - bits2, shift2, bits2)
             cum2 = np.cumsum(last)
             for r in rs:

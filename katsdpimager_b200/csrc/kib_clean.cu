@@ -717,21 +717,22 @@ abs_histogram_kernel(const float *__restrict__ image, int row_stride, long long 
         if (local[i] != 0) atomicAdd(&hist[i], local[i]);
 }
 
-// Second radix digit (bits shift .. shift+bits) of |pixel| for THREE adjacent values of the
-// leading digit (first_prefix, +1, +2) at once, plus the number of values whose leading digit
-// is smaller.  With a guess of the leading digit of the median (the previous estimate of the
-// same image is almost always within one bucket) this replaces the expensive first pass: the
-// second digit is spread evenly over its bins, so the shared-memory atomics do not collide.
+// Second radix digit (bits shift .. shift+bits) of |pixel| for `window` adjacent values of the
+// leading digit (first_prefix ...) at once, plus the number of values whose leading digit is
+// smaller.  With a guess of the leading digit of the median (the exponent of the previous
+// estimate of the same image: the window spans a factor of 256) this replaces the expensive
+// first pass: the second digit is spread evenly over its bins, so the shared-memory atomics do
+// not collide.
 __global__ void __launch_bounds__(256)
 abs_histogram_window_kernel(const float *__restrict__ image, int row_stride, long long pol_stride,
                             int inner_w, int inner_h, int P, int border,
-                            unsigned first_prefix, int prefix_shift, int shift, unsigned mask,
-                            unsigned *__restrict__ hist /* [3][mask + 1] */,
+                            unsigned first_prefix, unsigned window, int prefix_shift, int shift,
+                            unsigned mask, unsigned *__restrict__ hist /* [window][mask + 1] */,
                             unsigned long long *__restrict__ below)
 {
     extern __shared__ unsigned local[];
     const unsigned bins = mask + 1;
-    for (unsigned i = threadIdx.x; i < 3 * bins; i += blockDim.x) local[i] = 0;
+    for (unsigned i = threadIdx.x; i < window * bins; i += blockDim.x) local[i] = 0;
     __syncthreads();
     const int rows = inner_h * P;
     unsigned count_below = 0;
@@ -742,7 +743,7 @@ abs_histogram_window_kernel(const float *__restrict__ image, int row_stride, lon
         for (int x = threadIdx.x; x < inner_w; x += 256) {
             const unsigned bits = __float_as_uint(fabsf(__ldg(row + x)));
             const unsigned rel = (bits >> prefix_shift) - first_prefix;     // wraps when smaller
-            if (rel < 3u)
+            if (rel < window)
                 atomicAdd(&local[rel * bins + ((bits >> shift) & mask)], 1u);
             else
                 count_below += (bits >> prefix_shift) < first_prefix;
@@ -754,7 +755,7 @@ abs_histogram_window_kernel(const float *__restrict__ image, int row_stride, lon
     if ((threadIdx.x & 31) == 0 && count_below != 0)
         atomicAdd(below, (unsigned long long) count_below);
     __syncthreads();
-    for (unsigned i = threadIdx.x; i < 3 * bins; i += blockDim.x)
+    for (unsigned i = threadIdx.x; i < window * bins; i += blockDim.x)
         if (local[i] != 0) atomicAdd(&hist[i], local[i]);
 }
 
@@ -1074,7 +1075,7 @@ int kib_abs_histogram(const void *image, int row_stride, int64_t pol_stride,
                       uint32_t *hist, int dtype, kib_stream_t stream)
 {
     KIB_REQUIRE(dtype == KIB_F32, "kib_abs_histogram: only float32 images are supported");
-    KIB_REQUIRE(bits >= 1 && bits <= 12 && shift >= 0 && shift + bits <= 32,
+    KIB_REQUIRE(bits >= 1 && bits <= 13 && shift >= 0 && shift + bits <= 32,
                 "kib_abs_histogram: bad digit (shift %d, bits %d)", shift, bits);
     KIB_REQUIRE(prefix_bits >= 0 && prefix_bits + shift + bits <= 32,
                 "kib_abs_histogram: bad prefix");
@@ -1093,15 +1094,15 @@ int kib_abs_histogram(const void *image, int row_stride, int64_t pol_stride,
 
 int kib_abs_histogram_window(const void *image, int row_stride, int64_t pol_stride,
                              int width, int height, int num_pols, int border,
-                             uint32_t first_prefix, int prefix_bits, int shift, int bits,
-                             uint32_t *hist, unsigned long long *below, int dtype,
+                             uint32_t first_prefix, int window, int prefix_bits, int shift,
+                             int bits, uint32_t *hist, unsigned long long *below, int dtype,
                              kib_stream_t stream)
 {
     KIB_REQUIRE(dtype == KIB_F32, "kib_abs_histogram_window: only float32 images are supported");
-    KIB_REQUIRE(bits >= 1 && bits <= 11 && shift >= 0 && prefix_bits >= 1
-                && prefix_bits + shift + bits == 32,
-                "kib_abs_histogram_window: bad digits (prefix %d, shift %d, bits %d)",
-                prefix_bits, shift, bits);
+    KIB_REQUIRE(bits >= 1 && bits <= 13 && shift >= 0 && prefix_bits >= 1
+                && prefix_bits + shift + bits == 32 && window >= 1 && (window << bits) <= 8192,
+                "kib_abs_histogram_window: bad digits (prefix %d, shift %d, bits %d, window %d)",
+                prefix_bits, shift, bits, window);
     KIB_REQUIRE(hist != nullptr && below != nullptr, "kib_abs_histogram_window: null output");
     const int inner_w = width - 2 * border, inner_h = height - 2 * border;
     if (inner_w <= 0 || inner_h <= 0) return 0;
@@ -1109,10 +1110,10 @@ int kib_abs_histogram_window(const void *image, int row_stride, int64_t pol_stri
     const long long rows = (long long) inner_h * num_pols;
     int blocks = sm_count() * 8;
     if (blocks > rows) blocks = (int) rows;
-    abs_histogram_window_kernel<<<blocks, 256, 3 * (mask + 1) * sizeof(unsigned),
+    abs_histogram_window_kernel<<<blocks, 256, (size_t) window * (mask + 1) * sizeof(unsigned),
                                   as_stream(stream)>>>(
         static_cast<const float *>(image), row_stride, pol_stride, inner_w, inner_h, num_pols,
-        border, first_prefix, shift + bits, shift, mask, hist, below);
+        border, first_prefix, (unsigned) window, shift + bits, shift, mask, hist, below);
     KIB_CHECK_LAUNCH();
     return 0;
 }

@@ -37,6 +37,9 @@ inline int divup(int64_t a, int64_t b) { return (int) ((a + b - 1) / b); }
 
 int sm_count();
 
+// kib_grid.cu: frees the gridder's staging scratch of a stream (called when it is destroyed)
+void release_grid_scratch(cudaStream_t stream);
+
 template <typename Real> struct Complex2;
 template <> struct Complex2<float> { typedef float2 type; };
 template <> struct Complex2<double> { typedef double2 type; };

@@ -1055,6 +1055,24 @@ int grid_dispatch_f64(GridParams &prm, const GridConfig &cfg, int P, cudaStream_
 }  // namespace kib
 
 #if KIB_GRID_PART == 1
+namespace kib {
+// Called by kib_stream_destroy: the staging scratch of a stream dies with it (a recycled
+// stream handle must not inherit the buffer, and the memory must not leak).
+void release_grid_scratch(cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    for (auto it = g_scratch.begin(); it != g_scratch.end();) {
+        if (it->first.second == stream) {
+            if (it->second.data != nullptr) cudaFree(it->second.data);
+            it = g_scratch.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
+}  // namespace kib
+
 using namespace kib;
 
 extern "C" int kib_grid(void *grid, int grid_row_stride, int64_t grid_pol_stride, int grid_size,

@@ -147,7 +147,11 @@ int kib_stream_create(kib_stream_t *stream)
 
 int kib_stream_destroy(kib_stream_t stream)
 {
-    if (stream != nullptr) KIB_CUDA(cudaStreamDestroy(as_stream(stream)));
+    if (stream != nullptr) {
+        KIB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+        release_grid_scratch(as_stream(stream));
+        KIB_CUDA(cudaStreamDestroy(as_stream(stream)));
+    }
     return 0;
 }
 

@@ -364,6 +364,7 @@ class ImageToGrid(accel.OperationSequence):
         self.sparse_model = True
         self._factors = None
         self._fold = None
+        self._row_info = None
 
     def set_w(self, w):
         self._image_to_layer.set_w(w)
@@ -378,6 +379,23 @@ class ImageToGrid(accel.OperationSequence):
         stream = self.command_queue.stream
         n = layer.shape[1]
         context = self.command_queue.context
+        if self.sparse_model and _lib.load().kib_image_to_grid_sparse_supported(n, size, dtype):
+            # only rows with a non-zero pixel are transformed; the column pass never reads the
+            # others (taken as zero)
+            if self._row_info is None or self._row_info.shape[0] < 2 * n + 1:
+                self._row_info = accel.DeviceArray(context, (2 * n + 1,), np.int32)
+            for pol in range(polarizations):
+                with profile_device(self.command_queue, 'image_to_grid_rows'):
+                    _lib.call('kib_image_to_grid_rows_sparse', layer.ptr, layer.padded_shape[1],
+                              size, n, (image.ptr.value or 0) + pol * image_plane,
+                              image.padded_shape[2], kernel1d.ptr, float(op.lm_scale),
+                              float(op.lm_bias), float(op.w), self._row_info.ptr, dtype, stream)
+                with profile_device(self.command_queue, 'image_to_grid_columns'):
+                    _lib.call('kib_image_to_grid_columns_sparse',
+                              (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
+                              layer.ptr, layer.padded_shape[1], n, self._row_info.ptr, dtype,
+                              stream)
+            return
         factors = None
         if polarizations > 1 and not self.sparse_model:
             if self._factors is None or self._factors.shape != (n, n):

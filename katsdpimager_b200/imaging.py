@@ -98,6 +98,7 @@ class _RecordBlock:
         self.device = accel.DeviceArray(context, (max_vis * self.record_bytes,), np.uint8)
         self.staging = accel.HostArray((max_vis * self.record_bytes,), np.uint8, context=context)
         self.staging_event = None
+        self.upload_event = None
         self.source = None          # (address, count) of the records now on the device
 
     def matches(self, records):
@@ -143,9 +144,18 @@ class _RecordBlock:
             self.staging[:nbytes] = raw         # one contiguous copy
             src = self.staging
         _lib.call('kib_memcpy_h2d_async', self.device.ptr, src.ctypes.data, nbytes, queue.stream)
+        #: marks the end of the transfer: until then a pinned `records` array is being read by
+        #: the copy engine and must not be overwritten (:meth:`wait`)
+        self.upload_event = queue.enqueue_marker()
         if src is self.staging:
-            self.staging_event = queue.enqueue_marker()
+            self.staging_event = self.upload_event
         self.source = (address, count)
+
+    def wait(self):
+        """Block until the last upload has completed (a pinned source may then be reused)."""
+        if self.upload_event is not None:
+            self.upload_event.wait()
+            self.upload_event = None
 
     def unpack(self, count, uv=None, w_plane=None, weights=None, vis=None, vis_from_weights=False):
         def ptr(buffer):

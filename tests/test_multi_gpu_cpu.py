@@ -70,3 +70,40 @@ def test_gather_two_ranks_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert results == [True, True]
+
+
+def _cube_worker(rank, world, name, num_channels):
+    sys.path.insert(0, ROOT)
+    from katsdpimager_b200 import io
+    start, stop = distributed.channel_block(num_channels, rank, world)
+    cube = io.FitsCube(name)
+    for channel in range(start, stop):
+        plane = np.full(cube.shape[1:], float(channel + 1), np.float32)
+        plane[:, :, 0] = -float(channel + 1)            # marks the l = 0 column (flipped on disk)
+        cube.store(channel, plane)
+    cube.close()
+
+
+def test_cube_written_by_two_worker_processes(tmp_path):
+    """The multi-GPU 'gather': every worker process maps the same FITS cube and stores the
+    planes of its own channel block (katsdpimager_b200/io.py FitsCube; on a GPU box the store
+    is a device copy into the page-locked mapping).  No collective, no copy through rank 0."""
+    import torch.multiprocessing as mp
+    from katsdpimager_b200 import io, parameters as prm
+    fixed = prm.FixedImageParameters([1, 2], np.float32)
+    ip = prm.ImageParameters(fixed, wavelength=0.21, pixels=16, pixel_size=1e-4)
+    name = str(tmp_path / 'cube.fits')
+    num_channels = 5
+    io.FitsCube.create(name, num_channels, ip, 856e6, 1e6).close()
+    ctx = mp.get_context('spawn')
+    procs = [ctx.Process(target=_cube_worker, args=(r, 2, name, num_channels)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    header, data = io.read_fits(name)
+    assert data.shape == (num_channels, 2, 16, 16)
+    for channel in range(num_channels):
+        assert np.all(data[channel, :, :, :-1] == channel + 1)
+        assert np.all(data[channel, :, :, -1] == -(channel + 1))
