@@ -37,17 +37,20 @@ def main():
     host[:] = (rs.standard_normal(g.shape) + 1j * rs.standard_normal(g.shape))
     g.set(queue, host)
     op.num_vis = n
-    op()
-    queue.finish()
-    a = queue.enqueue_marker()
-    for _ in range(reps):
+    out = {'vis': n}
+    for route in (os.environ.get('DEGRID_ROUTES', 'thread,cached').split(',')):
+        os.environ['KIB_DEGRID_ROUTE'] = route
         op()
-    b = queue.enqueue_marker()
-    b.wait()
-    seconds = b.time_since(a) / reps
-    print(json.dumps({'vis': n, 'ms': seconds * 1e3, 'gvis_per_s': n / seconds / 1e9,
-                      'tflops': n * bench.flops_per_vis(7, 4) / seconds / 1e12}))
-
+        queue.finish()
+        a = queue.enqueue_marker()
+        for _ in range(reps):
+            op()
+        b = queue.enqueue_marker()
+        b.wait()
+        seconds = b.time_since(a) / reps
+        out[route] = {'ms': seconds * 1e3, 'gvis_per_s': n / seconds / 1e9,
+                      'tflops': n * bench.flops_per_vis(7, 4) / seconds / 1e12}
+    print(json.dumps(out))
 
 if __name__ == '__main__':
     main()
