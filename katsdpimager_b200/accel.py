@@ -97,6 +97,11 @@ class CommandQueue:
     def enqueue_marker(self):
         return Event(self.stream)
 
+    def enqueue_wait_for_events(self, events):
+        """Later work on this queue waits for `events` (of any queue) to complete."""
+        for event in events:
+            _lib.call('kib_stream_wait_event', self.stream, event._handle)
+
     def enqueue_zero_buffer(self, buffer):
         _lib.call('kib_memset_async', buffer.ptr, 0, buffer.nbytes, self.stream)
 

@@ -8,9 +8,15 @@
 // cross-thread reductions are needed at all when a thread owns a whole
 // visibility; consecutive threads hold consecutive samples of a baseline track,
 // whose footprints overlap almost entirely, so a warp's 32 gathers of tap (j,k)
-// fall in one or two 128-byte lines and are served by L1.  The separable kernel
-// row for v is hoisted out of the inner loop; all P polarizations share the
-// weight product.
+// fall in one or two 128-byte lines and are served by L1.  The L1 data pipe
+// delivers 128 bytes per clock whether or not the lanes' addresses coincide, so
+// every kernel here is bound by the number of bytes its lanes load per FMA: the
+// routes below differ in how few loads they issue besides the K x K x P grid
+// cells (taps in registers instead of one look-up per cell).  A register-cached
+// mirror of the gridder (8-lane groups holding their footprint rows, partial sums
+// reduced by shuffles) was built and measured at 0.61 ms against 0.31 ms for the
+// kernel below on the dense W slice of config 2 (profiles/r02_degrid.md); it is
+// in the history (commit 816e985), not in the library.
 #include "kib_common.cuh"
 #include <cstdlib>
 
@@ -120,277 +126,6 @@ degrid_kernel(const DegridParams prm)
         v.y = (float) ((Real) v.y - (Real) wt * sum[p].y);
         prm.vis[i * P + p] = v;
     }
-}
-
-// =====================================================================================
-// Fast path (float32, K <= 8): the mirror image of the gridder's register scheme.
-//
-// A *group* of 8 lanes walks a contiguous run of visibilities (one baseline track, mostly).
-// Lane t owns row slot t of the footprint and all MX >= K column slots of that row with the
-// gridder's cyclic assignment (column slot s always holds the grid column c >= u0 with
-// c == s mod MX, row slot t the row r >= v0 with r == t mod 8), and keeps those MX x P grid
-// cells in registers: consecutive visibilities of a track share their footprint, so a cell is
-// loaded from the grid once per *move* of the footprint instead of once per visibility.  Per
-// visibility a lane forms  wv[t] * sum_s wu[s] * cell[s][p]  (the taps come from doubled
-// tables in shared memory, as in grid_tma_kernel) and the 2 P partial sums are reduced over the
-// 8 lanes with a transposing butterfly (4 + 2 + 1 shuffles), which leaves component c of the
-// visibility in lane bitrev(c): the 8 lanes then update the 8 floats of vis[i] with one
-// 32-byte access.  Headers (origin, table offsets, move masks) are computed by the group
-// itself, 8 visibilities at a time, and passed through shared memory.
-constexpr int DG_LANES = 8;                 // lanes per group = row slots = batch length
-constexpr int DG_THREADS = 256;
-constexpr int DG_GROUPS = DG_THREADS / DG_LANES;
-constexpr int DG_LUT_SMEM_LIMIT = 96 * 1024;
-
-__device__ __forceinline__ unsigned dg_change_mask(int old_pos, int new_pos, int B)
-{
-    const int d = new_pos - old_pos;
-    if (d == 0) return 0u;
-    if (d >= B || -d >= B) return 0xffffu;
-    int start = (d > 0 ? old_pos : new_pos) % B;
-    const int count = d > 0 ? d : -d;
-    unsigned mask = 0;
-    for (int i = 0; i < count; i++) {
-        mask |= 1u << start;
-        if (++start == B) start = 0;
-    }
-    return mask;
-}
-
-template <int P, int MX>
-__global__ void __launch_bounds__(DG_THREADS, 2)
-degrid_cached_kernel(const DegridParams prm, int run)
-{
-    constexpr int BX = MX, BY = DG_LANES;
-    constexpr int NV = P == 1 ? 2 : (P == 2 ? 4 : 8);      // reduced values (2 P rounded up)
-    extern __shared__ __align__(16) unsigned char dg_smem[];
-    int4 *const hdr_all = reinterpret_cast<int4 *>(dg_smem);
-    float2 *const tabu = reinterpret_cast<float2 *>(hdr_all + DG_GROUPS * DG_LANES);
-    const int rows = prm.w_planes * prm.oversample;
-    const int vbase = rows * 2 * BX;
-    const int K = prm.kernel_width, G = prm.grid_size;
-    const int tid = threadIdx.x;
-
-    // doubled tap tables: entry e of a row holds tap e mod B (zero beyond K)
-    for (int e = tid; e < rows * 2 * (BX + BY); e += DG_THREADS) {
-        const bool is_v = e >= vbase;
-        const int f = is_v ? e - vbase : e;
-        const int period = is_v ? BY : BX;
-        const int row = f / (2 * period);
-        int d = f - row * 2 * period;
-        if (d >= period) d -= period;
-        tabu[e] = d < K ? __ldg(prm.lut + (long long) row * prm.lut_slice_stride
-                                + prm.lut_tap_offset + d)
-                        : make_float2(0.0f, 0.0f);
-    }
-    __syncthreads();
-
-    const int g = tid / DG_LANES;
-    const int t = tid % DG_LANES;
-    int4 *const hdr = hdr_all + g * DG_LANES;
-    const unsigned my_mask = ((1u << MX) - 1u) | (1u << (16 + t));
-    // component of the reduced visibility this lane ends up with
-    int comp = 0;
-#pragma unroll
-    for (int s = 0, half = NV / 2; half >= 1; s++, half /= 2)
-        if ((t >> s) & 1) comp += half;
-    const bool writer = t < NV && comp < 2 * P;
-
-    const long long group_id = (long long) blockIdx.x * DG_GROUPS + g;
-    const long long run_start = group_id * run;
-    long long run_end = run_start + run;
-    if (run_end > prm.num_vis) run_end = prm.num_vis;
-
-    float2 cell[MX][P];
-#pragma unroll
-    for (int i = 0; i < MX; i++)
-#pragma unroll
-        for (int p = 0; p < P; p++) cell[i][p] = make_float2(0.0f, 0.0f);
-    int carry_u = 0, carry_v = 0;
-    int rejected = 0;
-    const float2 *const grid = static_cast<const float2 *>(prm.grid);
-    float *const vis_f = reinterpret_cast<float *>(prm.vis);
-
-    for (int b = 0; b < run; b += DG_LANES) {
-        const long long batch_start = run_start + b;
-        {
-            // ---- header of visibility batch_start + t
-            const long long idx = batch_start + t;
-            const bool live = idx < run_end;
-            int u0 = 0, v0 = 0, w = 0, su = 0, sv = 0;
-            bool ok = false;
-            if (live) {
-                const short4 c = prm.uv[idx];
-                w = prm.w_plane[idx];
-                u0 = c.x - prm.uv_bias;
-                v0 = c.y - prm.uv_bias;
-                su = c.z;
-                sv = c.w;
-                ok = u0 >= 0 && v0 >= 0 && u0 + K <= G && v0 + K <= G
-                     && w >= 0 && w < prm.w_planes
-                     && su >= 0 && su < prm.oversample && sv >= 0 && sv < prm.oversample;
-                if (!ok) {
-                    // leaves vis untouched; harmless stand-in coordinates
-                    u0 = 0; v0 = 0; w = 0; su = 0; sv = 0;
-                    rejected++;
-                }
-            }
-            int pu = __shfl_up_sync(0xffffffffu, u0, 1, DG_LANES);
-            int pv = __shfl_up_sync(0xffffffffu, v0, 1, DG_LANES);
-            if (t == 0) { pu = carry_u; pv = carry_v; }
-            unsigned xm = 0, ym = 0;
-            if (live) {
-                if (b == 0 && t == 0) {
-                    xm = 0xffffu;           // first visibility of the run: every cell is new
-                    ym = 0xffffu;
-                } else {
-                    xm = dg_change_mask(pu, u0, BX);
-                    ym = dg_change_mask(pv, v0, BY);
-                }
-            }
-            const int ru = u0 % BX, rv = v0 % BY;
-            const int lutu = (w * prm.oversample + su) * 2 * BX + BX - ru;
-            const int lutv = vbase + (w * prm.oversample + sv) * 2 * BY + BY - rv;
-            hdr[t] = make_int4(u0 | (v0 << 16), lutu | (lutv << 16), (int) (xm | (ym << 16)),
-                               ru | (rv << 8) | (ok ? 0 : 0x10000));
-            // origin of the last live visibility of the batch (a dead tail ends the run)
-            carry_u = __shfl_sync(0xffffffffu, u0, DG_LANES - 1, DG_LANES);
-            carry_v = __shfl_sync(0xffffffffu, v0, DG_LANES - 1, DG_LANES);
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int e = 0; e < DG_LANES; e++) {
-            const int4 h = hdr[e];
-            const long long idx = batch_start + e;
-            const bool store = writer && !(h.w & 0x10000);
-            float vold = 0.0f, wt = 0.0f;
-            if (store) {
-                vold = vis_f[idx * (2 * P) + comp];
-                wt = __ldg(prm.weights + idx * P + (comp >> 1));
-            }
-            if ((unsigned) h.z & my_mask) {
-                // ---- the footprint moved: reload the cells that now hold another grid cell
-                const int u0 = h.x & 0xffff, v0 = (int) ((unsigned) h.x >> 16);
-                const int ru = h.w & 0xff, rv = (h.w >> 8) & 0xff;
-                int dy = t - rv;
-                if (dy < 0) dy += BY;
-                const int row = v0 + dy;
-                const bool row_changed = ((unsigned) h.z >> (16 + t)) & 1u;
-                const float2 *rp = grid + (long long) row * prm.grid_row_stride;
-#pragma unroll
-                for (int i = 0; i < MX; i++) {
-                    if (row_changed || (((unsigned) h.z >> i) & 1u)) {
-                        int dx = i - ru;
-                        if (dx < 0) dx += BX;
-                        const int col = u0 + dx;
-                        const bool inside = row < G && col < G;
-#pragma unroll
-                        for (int p = 0; p < P; p++)
-                            cell[i][p] = inside ? __ldg(rp + p * prm.grid_pol_stride + col)
-                                                : make_float2(0.0f, 0.0f);
-                    }
-                }
-            }
-            const float2 *urow = tabu + (h.y & 0xffff);
-            const float2 wv = tabu[((unsigned) h.y >> 16) + t];
-            float2 sum[P];
-#pragma unroll
-            for (int p = 0; p < P; p++) sum[p] = make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int i = 0; i < MX; i++) {
-                const float2 wu = urow[i];
-#pragma unroll
-                for (int p = 0; p < P; p++) {
-                    sum[p].x = fmaf(wu.x, cell[i][p].x, fmaf(-wu.y, cell[i][p].y, sum[p].x));
-                    sum[p].y = fmaf(wu.x, cell[i][p].y, fmaf(wu.y, cell[i][p].x, sum[p].y));
-                }
-            }
-            // weight = lut_v[j] * lut_u[k], no conjugate (grid.py:1150)
-            float r[NV];
-#pragma unroll
-            for (int i = 0; i < NV; i++) r[i] = 0.0f;
-#pragma unroll
-            for (int p = 0; p < P; p++) {
-                r[2 * p] = wv.x * sum[p].x - wv.y * sum[p].y;
-                r[2 * p + 1] = wv.x * sum[p].y + wv.y * sum[p].x;
-            }
-            // transposing butterfly: after step s a lane keeps the half of its values selected
-            // by bit s of its index, summed with its partner's
-#pragma unroll
-            for (int s = 0, half = NV / 2; half >= 1; s++, half /= 2) {
-                const bool up = (t >> s) & 1;
-#pragma unroll
-                for (int i = 0; i < half; i++) {
-                    const float send = up ? r[i] : r[i + half];
-                    const float keep = up ? r[i + half] : r[i];
-                    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << s);
-                }
-            }
-#pragma unroll
-            for (int m = NV; m < DG_LANES; m *= 2)
-                r[0] += __shfl_xor_sync(0xffffffffu, r[0], m);
-            if (store) vis_f[idx * (2 * P) + comp] = vold - wt * r[0];
-        }
-        __syncwarp();
-    }
-    if (rejected != 0 && prm.num_rejected != nullptr) atomicAdd(prm.num_rejected, rejected);
-}
-
-template <int P, int MX>
-static int launch_degrid_cached(const DegridParams &prm, size_t smem, cudaStream_t stream)
-{
-    // Runs long enough that the first load of a group's cells (MX x P per lane) is noise,
-    // short enough for two waves of blocks; small launches get shorter runs down to one batch.
-    const long long one_wave = (long long) sm_count() * 2 * DG_GROUPS;
-    long long run = (prm.num_vis + 2 * one_wave - 1) / (2 * one_wave);
-    if (run < 64) {
-        run = (prm.num_vis + one_wave - 1) / one_wave;
-        if (run > 64) run = 64;
-    }
-    if (run > 4096) run = 4096;
-    run = (run + DG_LANES - 1) / DG_LANES * DG_LANES;
-    const long long groups = (prm.num_vis + run - 1) / run;
-    const unsigned blocks = (unsigned) ((groups + DG_GROUPS - 1) / DG_GROUPS);
-    auto kernel = degrid_cached_kernel<P, MX>;
-    if (smem > 48 * 1024)
-        KIB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int) smem));
-    kernel<<<blocks, DG_THREADS, smem, stream>>>(prm, (int) run);
-    KIB_CHECK_LAUNCH();
-    return 0;
-}
-
-template <int P>
-static int dispatch_degrid_cached(const DegridParams &prm, int mx, size_t smem, cudaStream_t stream)
-{
-    switch (mx) {
-    case 4: return launch_degrid_cached<P, 4>(prm, smem, stream);
-    case 5: return launch_degrid_cached<P, 5>(prm, smem, stream);
-    case 6: return launch_degrid_cached<P, 6>(prm, smem, stream);
-    case 7: return launch_degrid_cached<P, 7>(prm, smem, stream);
-    case 8: return launch_degrid_cached<P, 8>(prm, smem, stream);
-    }
-    set_error("kib_degrid: no cached kernel for %d column slots", mx);
-    return -1;
-}
-
-// Returns 1 when the launch was not taken (caller falls through to the generic kernel).
-static int try_degrid_cached(const DegridParams &prm, int P, cudaStream_t stream)
-{
-    const int K = prm.kernel_width;
-    if (K > 8 || prm.grid_size >= 32768 || prm.grid_size < 16) return 1;
-    const int mx = K < 4 ? 4 : K;
-    const size_t rows = (size_t) prm.w_planes * prm.oversample;
-    const size_t entries = rows * 2 * (mx + DG_LANES);
-    const size_t smem = (size_t) DG_GROUPS * DG_LANES * sizeof(int4) + entries * sizeof(float2);
-    if (entries >= 65536 || entries * sizeof(float2) > (size_t) DG_LUT_SMEM_LIMIT) return 1;
-    switch (P) {
-    case 1: return dispatch_degrid_cached<1>(prm, mx, smem, stream);
-    case 2: return dispatch_degrid_cached<2>(prm, mx, smem, stream);
-    case 3: return dispatch_degrid_cached<3>(prm, mx, smem, stream);
-    case 4: return dispatch_degrid_cached<4>(prm, mx, smem, stream);
-    }
-    return 1;
 }
 
 // =====================================================================================
@@ -594,14 +329,14 @@ extern "C" int kib_degrid(const void *grid, int grid_row_stride, int64_t grid_po
     prm.kernel_width = kernel_width;
     prm.uv_bias = (kernel_width - 1) / 2 - grid_size / 2;
     if (dtype == KIB_F32) {
-        // "thread": scalar kernel, "cached": register-cached groups (K <= 8), default "vec"
+        // Measured on B200 (profiles/r02_degrid.md): supports up to 8 run the scalar kernel (K = 7
+        // specialised: taps in registers); wider supports keep a block of u taps in registers and
+        // read the grid as aligned 16-byte pairs when there is one polarization, as 8-byte cells
+        // otherwise.  KIB_DEGRID_ROUTE = thread | vec | hoist overrides the choice (probes).
         const char *route = getenv("KIB_DEGRID_ROUTE");
-        if (route && route[0] == 'c') {
-            const int rc = try_degrid_cached(prm, num_pols, as_stream(stream));
-            if (rc != 1) return rc;
-        }
-        if (!(route && route[0] == 't')) {
-            const bool wide = !(route && route[0] == 'h');      // "hoist": taps in registers, 8-byte loads
+        const bool pick_vec = route ? (route[0] == 'v' || route[0] == 'h') : kernel_width > 8;
+        if (pick_vec) {
+            const bool wide = route ? route[0] == 'v' : num_pols == 1;
             const int rc = try_degrid_vec(prm, num_pols, wide, as_stream(stream));
             if (rc != 1) return rc;
         }

@@ -395,9 +395,42 @@ class Imaging(accel.OperationSequence):
         with profile_device(self.command_queue, 'clear_' + name):
             self.buffer(name).zero(self.command_queue)
 
+    #: Zero the grid of the next W slice on a second stream while the current slice is still
+    #: being gridded / transformed (two grid buffers that swap at every clear_grid; the memset
+    #: is HBM-bound, the transform kernels are not).  False = the reference's in-order clear.
+    double_buffer_grid = True
+
     @profile_function()
     def clear_grid(self):
-        self._zero('grid')
+        current = self.buffer('grid')
+        if not self.double_buffer_grid or current is None:
+            self._zero('grid')
+            return
+        queue = self.command_queue
+        spare = getattr(self, '_grid_spare', None)
+        if spare is not None and (spare.shape != current.shape or spare.dtype != current.dtype
+                                  or spare.padded_shape != current.padded_shape):
+            spare = None                    # the caller bound a different grid buffer
+        if spare is None:
+            # first use: clear the bound grid in order, start clearing a second one on the side
+            self._side_queue = queue.context.create_command_queue()
+            self._grid_spare = accel.DeviceArray(queue.context, current.shape, current.dtype,
+                                                 current.padded_shape)
+            self._zero('grid')
+            with profile_device(self._side_queue, 'clear_grid'):
+                self._grid_spare.zero(self._side_queue)
+            self._spare_zeroed = self._side_queue.enqueue_marker()
+            return
+        # everything enqueued so far (the transform of the previous slice) is done with
+        # `current` when this marker completes; only then may the side stream wipe it
+        done = queue.enqueue_marker()
+        queue.enqueue_wait_for_events([self._spare_zeroed])
+        self.bind(grid=spare)
+        self._grid_spare = current
+        self._side_queue.enqueue_wait_for_events([done])
+        with profile_device(self._side_queue, 'clear_grid'):
+            current.zero(self._side_queue)
+        self._spare_zeroed = self._side_queue.enqueue_marker()
 
     @profile_function()
     def clear_dirty(self):

@@ -207,6 +207,7 @@ class FitsCube:
         self._pinned = None
         self._bounce = False
         self._staging = None
+        self._stored = None          # event: last overlapped device-to-host copy
         self._host = None
 
     @classmethod
@@ -254,10 +255,15 @@ class FitsCube:
             _lib.call('kib_host_unregister', self._pinned)
             self._pinned = None
 
-    def store_device(self, channel, image, queue):
+    def store_device(self, channel, image, queue, copy_queue=None):
         """Enqueue on `queue`: reorder `image` (DeviceArray, polarizations x N x N float32)
         into FITS order on the device and copy it into the mapped plane of `channel`.
-        The plane is valid once the queue has finished."""
+        The plane is valid once the queue has finished.
+
+        With `copy_queue` (pinned cube only) the device-to-host copy is enqueued there, behind
+        the reordering kernel, so that later work on `queue` overlaps it; the plane is valid
+        once the returned event has completed (the next call waits for it before it reuses
+        the staging buffer)."""
         from . import _lib, accel
         pols, height, width = image.shape
         if (pols, height, width) != self.shape[1:]:
@@ -265,10 +271,19 @@ class FitsCube:
         nbytes = pols * height * width * 4
         if self._staging is None or self._staging.shape[0] < nbytes:
             self._staging = accel.DeviceArray(queue.context, (nbytes,), np.uint8)
+        if self._stored is not None:
+            queue.enqueue_wait_for_events([self._stored])      # staging still being read
+            self._stored = None
         _lib.call('kib_fits_plane', self._staging.ptr, image.ptr, image.padded_shape[2],
                   image.padded_shape[1] * image.padded_shape[2], width, height, pols,
                   _lib.dtype_code(image.dtype), queue.stream)
         if self._pinned is not None:
+            if copy_queue is not None and copy_queue is not queue:
+                copy_queue.enqueue_wait_for_events([queue.enqueue_marker()])
+                _lib.call('kib_memcpy_d2h_async', self.data[channel].ctypes.data,
+                          self._staging.ptr, nbytes, copy_queue.stream)
+                self._stored = copy_queue.enqueue_marker()
+                return self._stored
             _lib.call('kib_memcpy_d2h_async', self.data[channel].ctypes.data, self._staging.ptr,
                       nbytes, queue.stream)
         else:
@@ -278,6 +293,7 @@ class FitsCube:
                       nbytes, queue.stream)
             queue.finish()
             self.data[channel].view(np.uint8).reshape(-1)[:] = self._host[:nbytes]
+        return queue.enqueue_marker()
 
     def flush(self):
         self.data.flush()

@@ -38,7 +38,7 @@ def main():
     g.set(queue, host)
     op.num_vis = n
     out = {'vis': n}
-    for route in (os.environ.get('DEGRID_ROUTES', 'thread,cached').split(',')):
+    for route in (os.environ.get('DEGRID_ROUTES', 'thread0,thread,vec,hoist').split(',')):
         os.environ['KIB_DEGRID_ROUTE'] = route
         op()
         queue.finish()
