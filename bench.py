@@ -49,7 +49,7 @@ W_PLANES = 16
 KERNEL_WIDTH = 7
 OVERSAMPLE = 8
 NUM_CHANNELS = 64
-VIS_BLOCK = 1 << 20
+VIS_BLOCK = int(os.environ.get('KIB_BENCH_VIS_BLOCK', 1 << 20))   # the reference's --vis-block default
 MAJOR = 3
 MINOR = 1000
 ROBUSTNESS = 0.0

@@ -255,6 +255,41 @@ int kib_image_to_grid_columns_sparse(void *grid_plane, int grid_row_stride, int 
                                      const void *scratch, int scratch_row_stride, int size,
                                      const int32_t *row_info, int dtype, kib_stream_t stream);
 
+/* Column occupancy of a W slice.  The reference transforms every column of the zero-padded layer
+ * (image.py:649-673, :716-740) although a visibility only touches kernel_width columns of the
+ * grid: the occupied groups of 8 columns are 3 - 87 % of a MeerKAT W slice.  `occupancy` is a
+ * bit mask owned by the caller, (grid_size / 8 + 31) / 32 + 1 words, bit g = columns
+ * [8 g, 8 g + 8) may hold data.  kib_column_occupancy ORs the footprints (origin as in kib_grid:
+ * u - ((K - 1) / 2 - G / 2)) of num_vis coordinates into it; `uv` points at the first int16 u,
+ * consecutive visibilities stride_bytes apart (8 for the uv slot, the record size for
+ * preprocessed records).  The *_occ entry points are kib_grid_to_image_columns / _rows and
+ * kib_image_to_grid_columns (row_info as in kib_image_to_grid_columns_sparse, or NULL) restricted
+ * to the occupied groups: grid -> image takes every other column of the grid as zero without
+ * reading it (the caller promises that it is), image -> grid computes the occupied groups and
+ * leaves the other columns of the grid unspecified (untouched, or computed when they share a
+ * tile with an occupied group; the caller promises not to read them).  Results on the occupied
+ * columns are bit-identical to the dense entry points. */
+int kib_column_occupancy(const void *uv, int64_t stride_bytes, int64_t num_vis, int kernel_width,
+                         int grid_size, uint32_t *occupancy, kib_stream_t stream);
+int kib_grid_to_image_columns_occ(void *scratch, int scratch_row_stride, int size,
+                                  const void *grid_plane, int grid_row_stride, int grid_size,
+                                  void *fold_scratch, const uint32_t *occupancy, int dtype,
+                                  kib_stream_t stream);
+/* The row pass wants the mask per first-stage butterfly: kib_row_presence turns `occupancy` into
+ * `presence` (size / 16 uint16, owned by the caller) for an image of size^2 pixels;
+ * kib_grid_to_image_rows_occ takes that table. */
+int kib_row_presence(const uint32_t *occupancy, int grid_size, int size, uint16_t *presence,
+                     kib_stream_t stream);
+int kib_grid_to_image_rows_occ(void *image_plane, int image_row_stride,
+                               const void *scratch, int scratch_row_stride, int grid_size, int size,
+                               const void *kernel1d, double lm_scale, double lm_bias, double w,
+                               void *factors, int factor_mode, const uint16_t *presence,
+                               int dtype, kib_stream_t stream);
+int kib_image_to_grid_columns_occ(void *grid_plane, int grid_row_stride, int grid_size,
+                                  const void *scratch, int scratch_row_stride, int size,
+                                  void *fold_scratch, const int32_t *row_info,
+                                  const uint32_t *occupancy, int dtype, kib_stream_t stream);
+
 /* kib_image_to_layer replaces image_to_layer.mako (oracle image.py:836-843):
  *   layer[ifftshift(y,x)] = image[y][x] / (kernel1d[y]*kernel1d[x]*n) * exp(-2 pi i w (n-1)) */
 int kib_image_to_layer(void *layer, int layer_row_stride,

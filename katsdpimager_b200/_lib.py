@@ -81,6 +81,11 @@ SIGNATURES = {
     'kib_image_to_grid_rows_sparse': [_vp, _i, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _vp],
     'kib_image_to_grid_columns_sparse': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
+    'kib_column_occupancy': [_vp, c_int64, c_int64, _i, _i, _vp, _vp],
+    'kib_row_presence': [_vp, _i, _i, _vp, _vp],
+    'kib_grid_to_image_columns_occ': [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp],
+    'kib_grid_to_image_rows_occ': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _vp, _i, _vp],
+    'kib_image_to_grid_columns_occ': [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     'kib_scale': [_vp, _i, _i64, _i, _i, _i, POINTER(c_double), _i, _vp],
     'kib_add_image': [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp],
     'kib_apply_primary_beam': [_vp, _i, _i64, _vp, _i, _i, _i, _d, _d, _i, _vp],
@@ -162,7 +167,8 @@ _ONE_KERNEL = frozenset([
     'kib_update_tiles', 'kib_find_peak', 'kib_subtract_psf', 'kib_psf_patch',
     'kib_abs_histogram', 'kib_abs_histogram_window', 'kib_rank', 'kib_grid_weights', 'kib_mean_weight',
     'kib_density_weights', 'kib_fill', 'kib_fits_plane', 'kib_fourier_beam', 'kib_predict', 'kib_fp32_peak_kernel',
-    'kib_unpack_records', 'kib_grid_to_image_rows', 'kib_image_to_grid_rows'])
+    'kib_unpack_records', 'kib_grid_to_image_rows', 'kib_image_to_grid_rows',
+    'kib_grid_to_image_rows_occ', 'kib_column_occupancy', 'kib_row_presence'])
 
 #: number of hand-written kernels launched through this module (cuFFT and memset/memcpy
 #: are not counted); bench.py reports the difference over its timed region
@@ -175,9 +181,9 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
     if name in _ONE_KERNEL:
         kernel_launches += 1
-    elif name == 'kib_grid_to_image_columns':
+    elif name in ('kib_grid_to_image_columns', 'kib_grid_to_image_columns_occ'):
         kernel_launches += load().kib_grid_to_image_columns_kernels(int(args[2]))
-    elif name == 'kib_image_to_grid_columns':
+    elif name in ('kib_image_to_grid_columns', 'kib_image_to_grid_columns_occ'):
         kernel_launches += load().kib_grid_to_image_columns_kernels(int(args[5]))
     elif name == 'kib_image_to_grid_rows_sparse':
         kernel_launches += 2                 # row classification + transforms of non-empty rows

@@ -257,6 +257,35 @@ def _check_grid(grid, layer):
     return polarizations, width
 
 
+def occupancy_words(grid_size):
+    """Length (uint32 words) of the column-occupancy mask of a grid (kib_column_occupancy)."""
+    return (grid_size // 8 + 31) // 32 + 1
+
+
+def column_occupancy(command_queue, uv, num_vis, kernel_width, grid_size, stride_bytes=8,
+                     out=None):
+    """Mark the groups of 8 grid columns that the footprints of `num_vis` visibilities cover.
+
+    `uv` is a device pointer (or DeviceArray) to the first int16 u coordinate, consecutive
+    visibilities `stride_bytes` apart.  ORs into `out` (a zeroed uint32 DeviceArray of
+    :func:`occupancy_words` words is made if None) and returns it."""
+    if out is None:
+        out = accel.DeviceArray(command_queue.context, (occupancy_words(grid_size),), np.uint32)
+        out.zero(command_queue)
+    ptr = uv.ptr if hasattr(uv, 'ptr') else uv
+    _lib.call('kib_column_occupancy', ptr, int(stride_bytes), int(num_vis), int(kernel_width),
+              int(grid_size), out.ptr, command_queue.stream)
+    return out
+
+
+def _check_occupancy(occupancy, grid_size):
+    if occupancy is None:
+        return None
+    if occupancy.dtype != np.uint32 or occupancy.shape[0] < occupancy_words(grid_size):
+        raise ValueError('occupancy must hold {} uint32 words'.format(occupancy_words(grid_size)))
+    return occupancy
+
+
 class GridToImage(accel.OperationSequence):
     """grid -> image for every polarization (reference image.py:609-673).
 
@@ -283,6 +312,10 @@ class GridToImage(accel.OperationSequence):
         #: use the fused pruned transform (kib_grid_to_image) when the library supports
         #: the size (single precision, power-of-two images of 2048..16384 pixels)
         self.fused = True
+        #: column occupancy of the grid (:func:`column_occupancy`), or None.  When set, the
+        #: caller promises that the grid is zero outside the occupied column groups; the fused
+        #: transform then skips them (bit-identical image).
+        self.occupancy = None
         self._factors = None
         self._fold = None
 
@@ -309,17 +342,40 @@ class GridToImage(accel.OperationSequence):
         fold_bytes = _lib.grid_to_image_fold_bytes(n, size)
         if self._fold is None or self._fold.shape[0] < fold_bytes:
             self._fold = accel.DeviceArray(self.command_queue.context, (fold_bytes,), np.uint8)
+        occ = _check_occupancy(self.occupancy, size)
+        presence = None
+        if occ is not None:
+            # the row pass's view of the mask, made once per mask and image size
+            tables = occ.__dict__.setdefault('_row_presence', {})
+            presence = tables.get((n, size))
+            if presence is None:
+                presence = accel.DeviceArray(self.command_queue.context, (n // 16,), np.uint16)
+                _lib.call('kib_row_presence', occ.ptr, size, n, presence.ptr, stream)
+                tables[(n, size)] = presence
         for pol in range(polarizations):
+            mode = 0 if factors is None else (1 if pol == 0 else 2)
+            grid_plane = (grid.ptr.value or 0) + pol * plane_bytes
+            image_ptr = (image.ptr.value or 0) + pol * image_plane
+            if occ is not None:
+                with profile_device(self.command_queue, 'grid_to_image_columns'):
+                    _lib.call('kib_grid_to_image_columns_occ', layer.ptr, layer.padded_shape[1],
+                              layer.shape[1], grid_plane, grid.padded_shape[2], size,
+                              self._fold.ptr, occ.ptr, dtype, stream)
+                with profile_device(self.command_queue, 'grid_to_image_rows'):
+                    _lib.call('kib_grid_to_image_rows_occ', image_ptr, image.padded_shape[2],
+                              layer.ptr, layer.padded_shape[1], size, layer.shape[1],
+                              kernel1d.ptr, float(op.lm_scale), float(op.lm_bias), float(op.w),
+                              factors, mode, presence.ptr, dtype, stream)
+                continue
             with profile_device(self.command_queue, 'grid_to_image_columns'):
                 _lib.call('kib_grid_to_image_columns', layer.ptr, layer.padded_shape[1],
-                          layer.shape[1], (grid.ptr.value or 0) + pol * plane_bytes,
-                          grid.padded_shape[2], size, self._fold.ptr, dtype, stream)
+                          layer.shape[1], grid_plane, grid.padded_shape[2], size,
+                          self._fold.ptr, dtype, stream)
             with profile_device(self.command_queue, 'grid_to_image_rows'):
-                _lib.call('kib_grid_to_image_rows',
-                          (image.ptr.value or 0) + pol * image_plane, image.padded_shape[2],
+                _lib.call('kib_grid_to_image_rows', image_ptr, image.padded_shape[2],
                           layer.ptr, layer.padded_shape[1], size, layer.shape[1], kernel1d.ptr,
                           float(op.lm_scale), float(op.lm_bias), float(op.w),
-                          factors, 0 if factors is None else (1 if pol == 0 else 2), dtype, stream)
+                          factors, mode, dtype, stream)
 
     def _run(self):
         grid = self.buffer('grid')
@@ -362,6 +418,10 @@ class ImageToGrid(accel.OperationSequence):
         #: entirely zero are not transformed.  Always exact; only the speed depends on it
         #: (a dense image is transformed faster with False: shared per-pixel factors).
         self.sparse_model = True
+        #: column occupancy (:func:`column_occupancy`) of the visibilities that will be
+        #: degridded from the grid, or None.  When set, only the occupied column groups of the
+        #: grid are computed; the others keep whatever they held.
+        self.occupancy = None
         self._factors = None
         self._fold = None
         self._row_info = None
@@ -379,6 +439,7 @@ class ImageToGrid(accel.OperationSequence):
         stream = self.command_queue.stream
         n = layer.shape[1]
         context = self.command_queue.context
+        occ = _check_occupancy(self.occupancy, size)
         if self.sparse_model and _lib.load().kib_image_to_grid_sparse_supported(n, size, dtype):
             # only rows with a non-zero pixel are transformed; the column pass never reads the
             # others (taken as zero)
@@ -391,10 +452,16 @@ class ImageToGrid(accel.OperationSequence):
                               image.padded_shape[2], kernel1d.ptr, float(op.lm_scale),
                               float(op.lm_bias), float(op.w), self._row_info.ptr, dtype, stream)
                 with profile_device(self.command_queue, 'image_to_grid_columns'):
-                    _lib.call('kib_image_to_grid_columns_sparse',
-                              (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
-                              layer.ptr, layer.padded_shape[1], n, self._row_info.ptr, dtype,
-                              stream)
+                    if occ is not None:
+                        _lib.call('kib_image_to_grid_columns_occ',
+                                  (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2],
+                                  size, layer.ptr, layer.padded_shape[1], n, None,
+                                  self._row_info.ptr, occ.ptr, dtype, stream)
+                    else:
+                        _lib.call('kib_image_to_grid_columns_sparse',
+                                  (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2],
+                                  size, layer.ptr, layer.padded_shape[1], n, self._row_info.ptr,
+                                  dtype, stream)
             return
         factors = None
         if polarizations > 1 and not self.sparse_model:
@@ -415,9 +482,16 @@ class ImageToGrid(accel.OperationSequence):
                           kernel1d.ptr, float(op.lm_scale), float(op.lm_bias), float(op.w),
                           factors, mode, dtype, stream)
             with profile_device(self.command_queue, 'image_to_grid_columns'):
-                _lib.call('kib_image_to_grid_columns',
-                          (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2], size,
-                          layer.ptr, layer.padded_shape[1], n, self._fold.ptr, dtype, stream)
+                if occ is not None:
+                    _lib.call('kib_image_to_grid_columns_occ',
+                              (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2],
+                              size, layer.ptr, layer.padded_shape[1], n, self._fold.ptr, None,
+                              occ.ptr, dtype, stream)
+                else:
+                    _lib.call('kib_image_to_grid_columns',
+                              (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2],
+                              size, layer.ptr, layer.padded_shape[1], n, self._fold.ptr, dtype,
+                              stream)
 
     def _run(self):
         grid = self.buffer('grid')

@@ -460,16 +460,26 @@ class Imaging(accel.OperationSequence):
         self._continuum_predict.set_sky_model(sky_model, phase_centre)
 
     @profile_function()
-    def grid_to_image(self, w):
+    def grid_to_image(self, w, occupancy=None):
+        """`occupancy` (not in the reference; :func:`.image.column_occupancy` of everything
+        gridded since :meth:`clear_grid`) lets the transform skip the empty columns."""
         self._grid_to_image.set_w(w)
+        self._grid_to_image.occupancy = occupancy
         self._grid_to_image()
 
     @profile_function()
-    def model_to_grid(self, w):
+    def model_to_grid(self, w, occupancy=None):
+        """`occupancy` (not in the reference): column occupancy of the visibilities that will be
+        predicted from the grid; the other columns of the grid are not computed."""
         if self._image_to_grid is None:
             raise RuntimeError('Can only use model_to_grid with degridding')
         self._image_to_grid.set_w(w)
+        self._image_to_grid.occupancy = occupancy
         self._image_to_grid()
+
+    @property
+    def kernel_width(self):
+        return self.template.fixed_grid_parameters.kernel_width
 
     @profile_function()
     def model_to_predict(self):

@@ -119,6 +119,7 @@ class ResidentVisibilities:
         queue = self.command_queue
         keepalive = []
         self.h2d_bytes = 0
+        self.__dict__.pop('_occupancy', None)       # new records, new footprints
         base = self.buffer.ptr.value or 0
         for records, offset in zip(slices, self.offsets):
             if len(records) == 0:
@@ -187,6 +188,19 @@ class ResidentVisibilities:
                       self.num_polarizations, ptr(uv), ptr(w_plane), ptr(weights), ptr(vis),
                       int(vis_from_weights), queue.stream)
 
+    def occupancy(self, queue, w_slice, kernel_width, grid_size):
+        """Column occupancy of a W slice (:func:`.image.column_occupancy`): computed on the
+        device from the resident records the first time it is asked for, then kept."""
+        from . import image
+        cache = self.__dict__.setdefault('_occupancy', {})
+        key = (w_slice, kernel_width, grid_size)
+        if key not in cache:
+            base = (self.buffer.ptr.value or 0) + self.offsets[w_slice]
+            with profile_device(queue, 'column_occupancy'):
+                cache[key] = image.column_occupancy(queue, base, self.counts[w_slice],
+                                                    kernel_width, grid_size, self.record_bytes)
+        return cache[key]
+
     def feed(self, imager, w_slice, start, count, field, with_weights):
         """Make records [start, start + count) the imager's current chunk."""
         imager.set_resident(self, w_slice, start, count, field, with_weights)
@@ -239,7 +253,8 @@ def make_weights(imager, vis, weight_type, vis_block):
     return imager.finalize_weights()
 
 
-def make_dirty(imager, vis, field, mid_w, vis_block, degrid, full_cycle=False):
+def make_dirty(imager, vis, field, mid_w, vis_block, degrid, full_cycle=False,
+               use_occupancy=True):
     """reference frontend.make_dirty (frontend.py:110-149) over resident records.
 
     `field` is ``'weights'`` (PSF: the weights are gridded as visibilities,
@@ -250,21 +265,37 @@ def make_dirty(imager, vis, field, mid_w, vis_block, degrid, full_cycle=False):
     for w_slice in range(vis.num_w_slices):
         if vis.len(w_slice) == 0:
             continue
+        # which columns of the grid this slice touches (resident records only): the transforms
+        # skip the others -- same images, see image.column_occupancy
+        occupancy = None
+        if use_occupancy and hasattr(vis, 'occupancy') and hasattr(imager, 'kernel_width'):
+            occupancy = vis.occupancy(imager.command_queue, w_slice, imager.kernel_width,
+                                      imager.buffer('grid').shape[-1])
         if full_cycle and degrid:
-            imager.model_to_grid(mid_w[w_slice])
+            if occupancy is not None:
+                imager.model_to_grid(mid_w[w_slice], occupancy=occupancy)
+            else:
+                imager.model_to_grid(mid_w[w_slice])
         imager.clear_grid()
         for start, count in vis.chunks(w_slice, vis_block):
             vis.feed(imager, w_slice, start, count, field, full_cycle)
             if full_cycle:
                 imager.predict(mid_w[w_slice])
             imager.grid()
-        imager.grid_to_image(mid_w[w_slice])
+        if occupancy is not None:
+            imager.grid_to_image(mid_w[w_slice], occupancy=occupancy)
+        else:
+            imager.grid_to_image(mid_w[w_slice])
 
 
 def process_channel(imager, vis, image_parameters, grid_parameters, clean_parameters,
-                    weight_parameters, major, vis_block, restore=None, out=None):
+                    weight_parameters, major, vis_block, restore=None, out=None,
+                    use_occupancy=True):
     """reference frontend.process_channel (frontend.py:494-641) for one channel whose
     visibilities are resident.
+
+    `use_occupancy`: let the grid <-> image transforms skip the grid columns no visibility of
+    the W slice touches (:meth:`ResidentVisibilities.occupancy`; same images).
 
     `restore`, if given, is called as ``restore(imager, psf_patch)`` after the last major
     cycle and before the model is added back (the restoring-beam convolution,
@@ -291,7 +322,7 @@ def process_channel(imager, vis, image_parameters, grid_parameters, clean_parame
     # PSF (frontend.py:507-540)
     slice_w_step = float(gp.fixed.max_w / ip.wavelength / (gp.w_slices - 0.5))
     mid_w = np.arange(gp.w_slices) * slice_w_step
-    make_dirty(imager, vis, 'weights', mid_w, vis_block, degrid)
+    make_dirty(imager, vis, 'weights', mid_w, vis_block, degrid, use_occupancy=use_occupancy)
     stats['passes'] += 1
     dirty = imager.buffer('dirty')
     # pinned scratch is kept on the imager: freeing page-locked memory synchronises the device
@@ -318,7 +349,8 @@ def process_channel(imager, vis, image_parameters, grid_parameters, clean_parame
     stats['minor'] = 0
     noise = None
     for i in range(major):
-        make_dirty(imager, vis, 'vis', mid_w, vis_block, degrid, full_cycle=i != 0)
+        make_dirty(imager, vis, 'vis', mid_w, vis_block, degrid, full_cycle=i != 0,
+                   use_occupancy=use_occupancy)
         stats['passes'] += 1
         if i == 0 and restore is not None and hasattr(restore, 'fit'):
             restore.fit()                       # host-side beam fit while the device grids

@@ -488,3 +488,127 @@ def test_image_to_grid_sparse_model_rows(gpu, oracle):
     expected = oracle.image_to_grid(model, kernel1d, lm_scale, lm_bias, np.float64(21.5),
                                     grid_size=grid_size)
     assert np.abs(results[0] - expected).max() / np.abs(expected).max() < 2e-5
+
+
+def _occupancy_mask(occupied_groups, grid_size):
+    words = np.zeros(image.occupancy_words(grid_size), np.uint32)
+    for g in occupied_groups:
+        words[g >> 5] |= np.uint32(1) << np.uint32(g & 31)
+    return words
+
+
+def test_column_occupancy_kernel(gpu):
+    """kib_column_occupancy against numpy: footprints u0 .. u0 + K - 1 with the gridder's
+    origin, out-of-range coordinates ignored, both from a packed uv array (stride 8) and from
+    inside preprocessed records (stride 12 + 12 P)."""
+    context, queue = gpu
+    rs = RandomState(5)
+    for grid_size, K in ((1230, 7), (4922, 7), (9864, 32), (512, 60)):
+        n = 5000
+        bias = (K - 1) // 2 - grid_size // 2
+        limit = grid_size // 2
+        u = rs.randint(-limit // 3, limit // 2, n).astype(np.int16)
+        u[:20] = rs.randint(-limit - 40, -limit + 40, 20)          # around / beyond the left edge
+        u[20:40] = rs.randint(limit - 70, limit + 40, 20)          # around / beyond the right edge
+        expected = set()
+        for x in u.astype(int):
+            u0 = x - bias
+            if u0 < 0 or u0 + K > grid_size:
+                continue
+            expected.update(range(u0 >> 3, ((u0 + K - 1) >> 3) + 1))
+        want = _occupancy_mask(expected, grid_size)
+        for stride in (8, 60):
+            raw = np.zeros((n, stride), np.uint8)
+            raw[:, :2] = u.view(np.uint8).reshape(n, 2)
+            raw[:, 2:] = rs.randint(0, 255, (n, stride - 2))
+            dev = accel.DeviceArray(context, raw.shape, np.uint8)
+            dev.set(queue, raw)
+            occ = image.column_occupancy(queue, dev, n, K, grid_size, stride)
+            np.testing.assert_array_equal(occ.get(queue), want)
+
+
+@pytest.mark.parametrize('pixels,grid_size,pols', [(2048, 1230, 2), (4096, 2470, 1),
+                                                   (8192, 4922, 2), (16384, 9864, 1)])
+def test_grid_to_image_occupancy(gpu, pixels, grid_size, pols):
+    """A grid that is zero outside some groups of 8 columns, transformed with and without its
+    occupancy mask: bit-identical images, and the masked route must not even read the other
+    columns (they are filled with NaN for it)."""
+    context, queue = gpu
+    g2i, grid, kernel1d, lm_scale, lm_bias = _fused_case(
+        context, queue, pixels, grid_size, pols, 21, True)
+    rs = RandomState(22)
+    groups = (grid_size + 7) // 8
+    occupied = sorted(set(rs.randint(0, groups, groups // 3)) | {0, groups - 1})
+    keep = np.zeros(grid_size, bool)
+    for g in occupied:
+        keep[8 * g:8 * g + 8] = True
+    sparse = np.where(keep[np.newaxis, np.newaxis, :], grid, 0).astype(np.complex64)
+    g2i.set_w(133.5)
+    g2i.buffer('grid').set(queue, sparse)
+    g2i.buffer('image').zero(queue)
+    g2i()
+    dense = g2i.buffer('image').get(queue)
+    poisoned = np.where(keep[np.newaxis, np.newaxis, :], grid, np.nan + 1j * np.nan)
+    g2i.buffer('grid').set(queue, poisoned.astype(np.complex64))
+    # stale data in the half-transformed plane must not matter either
+    layer = g2i.buffer('layer')
+    layer.set(queue, np.full(layer.shape, np.nan, layer.dtype))
+    occ = accel.DeviceArray(context, (image.occupancy_words(grid_size),), np.uint32)
+    occ.set(queue, _occupancy_mask(occupied, grid_size))
+    g2i.occupancy = occ
+    g2i.buffer('image').zero(queue)
+    g2i()
+    masked = g2i.buffer('image').get(queue)
+    assert np.isfinite(masked).all()
+    np.testing.assert_array_equal(masked, dense)
+    assert np.abs(dense).max() > 0
+
+
+@pytest.mark.parametrize('pixels,grid_size,sparse_model', [(2048, 1230, True), (2048, 1230, False),
+                                                           (8192, 4922, True), (16384, 9864, False)])
+def test_image_to_grid_occupancy(gpu, pixels, grid_size, sparse_model):
+    """image -> grid restricted to an occupancy mask: the occupied column groups are
+    bit-identical to the dense transform; every other column is either left untouched or (when
+    it shares a 16-column tile with an occupied group) computed all the same."""
+    context, queue = gpu
+    from katsdpimager_b200 import _lib
+    rs = RandomState(31)
+    pols = 2
+    lm_scale = 0.2 / pixels
+    lm_bias = -lm_scale * pixels / 2
+    template = image.GridImageTemplate(context, np.float32)
+    plan = template.make_fft_plan((pixels, pixels), (pixels, pixels))
+    i2g = template.instantiate_image_to_grid(queue, (pols, grid_size, grid_size),
+                                             lm_scale, lm_bias, plan)
+    i2g.ensure_all_bound()
+    i2g.sparse_model = sparse_model
+    if sparse_model and not _lib.load().kib_image_to_grid_sparse_supported(
+            pixels, grid_size, _lib.dtype_code(np.dtype(np.complex64))):
+        pytest.skip('no sparse route at this size')
+    model = np.zeros((pols, pixels, pixels), np.float32)
+    model[0, rs.randint(0, pixels, 60), rs.randint(0, pixels, 60)] = rs.uniform(0.5, 2.0, 60)
+    model[1, rs.randint(0, pixels, 9), rs.randint(0, pixels, 9)] = rs.uniform(-2.0, -0.5, 9)
+    i2g.buffer('image').set(queue, model)
+    i2g.buffer('kernel1d').set(queue, rs.uniform(1.0, 2.0, pixels).astype(np.float32))
+    i2g.set_w(21.5)
+    i2g()
+    dense = i2g.buffer('grid').get(queue)
+    groups = (grid_size + 7) // 8
+    occupied = sorted(set(rs.randint(0, groups, groups // 4)) | {0, groups - 1})
+    keep = np.zeros(grid_size, bool)
+    for g in occupied:
+        keep[8 * g:8 * g + 8] = True
+    occ = accel.DeviceArray(context, (image.occupancy_words(grid_size),), np.uint32)
+    occ.set(queue, _occupancy_mask(occupied, grid_size))
+    i2g.occupancy = occ
+    sentinel = np.complex64(7 + 7j)
+    i2g.buffer('grid').set(queue, np.full((pols, grid_size, grid_size), sentinel, np.complex64))
+    i2g()
+    masked = i2g.buffer('grid').get(queue)
+    np.testing.assert_array_equal(masked[:, :, keep], dense[:, :, keep])
+    rest = masked[:, :, ~keep]
+    untouched = (rest == sentinel).all(axis=(0, 1))
+    computed = (rest == dense[:, :, ~keep]).all(axis=(0, 1))
+    assert (untouched | computed).all()
+    assert untouched.sum() > 0.4 * rest.shape[2]
+    assert np.abs(dense).max() > 0
