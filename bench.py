@@ -105,6 +105,25 @@ def flops_per_vis(kernel_width, pols):
     return kernel_width ** 2 * (8 * pols + 6)
 
 
+def column_occupancy_fractions(slices, grid_size):
+    """Fraction of the groups of 8 grid columns that the footprints of each W slice cover
+    (host restatement of kib_column_occupancy, for the byte accounting of the rooflines)."""
+    groups = (grid_size + 7) // 8
+    bias = (KERNEL_WIDTH - 1) // 2 - grid_size // 2
+    out = []
+    for s in slices:
+        if len(s) == 0:
+            out.append(0.0)
+            continue
+        u0 = np.unique(np.asarray(s.uv[:, 0], np.int64)) - bias
+        u0 = u0[(u0 >= 0) & (u0 + KERNEL_WIDTH <= grid_size)]
+        mask = np.zeros(groups + 1, bool)
+        mask[u0 >> 3] = True
+        mask[(u0 + KERNEL_WIDTH - 1) >> 3] = True       # K <= 8: at most two groups
+        out.append(float(mask[:groups].sum()) / groups)
+    return out
+
+
 def step_work(slices):
     """Units of work in one step, shared by both arms."""
     total_vis = sum(len(s) for s in slices)
@@ -708,23 +727,33 @@ def run_gpu(args, ranks):
                 'vis_per_sec': vis_per_launch / (secs / count),
                 'avg_launch_ms': secs / count * 1e3, 'ms_per_step': secs / args.steps * 1e3}
 
+    # Column occupancy (katsdpimager_b200.image.column_occupancy): the transforms only touch the
+    # groups of 8 grid columns a W slice's footprints cover.  Every non-empty slice is
+    # transformed equally often, so the launch-averaged occupied fraction is the plain mean.
+    occupied = column_occupancy_fractions(slices, grid_size)
+    occ = float(np.mean([f for f in occupied if f > 0.0]))
     rows_roofline = hbm_roofline(
-        'grid_to_image_rows', 'rows_kernel<8192,512,16,16,2> (kib_gridfft.cu)',
-        8.0 * N * G + 8.0 * N * N, 'fused_rows_dram_bytes_per_launch',
-        'algorithmic bytes = 8 N G (half-transformed plane) + 8 N^2 (image read + write)')
+        'grid_to_image_rows', 'rows_kernel<8192,512,16,16,2,MODE,masked> (kib_gridfft.cu)',
+        8.0 * N * G * occ + 8.0 * N * N, 'fused_rows_dram_bytes_per_launch',
+        'algorithmic bytes = 8 N G f (occupied columns of the half-transformed plane, mean '
+        'occupied fraction f = {:.3f}) + 8 N^2 (image read + write); the kernel is bound by its '
+        'N-point FFTs (issue slots / shared memory), not by these bytes'.format(occ))
     rooflines = {
         'grid_to_image_columns': hbm_roofline(
             'grid_to_image_columns', 'columns_cluster_kernel<8,1024,8> (kib_gridfft.cu)',
-            8.0 * G * G + 8.0 * N * G, 'fused_columns_dram_bytes_per_launch',
-            'algorithmic bytes = 8 G^2 (grid plane) + 8 N G (half-transformed plane written)'),
+            (8.0 * G * G + 8.0 * N * G) * occ, 'fused_columns_dram_bytes_per_launch',
+            'algorithmic bytes = (8 G^2 (grid plane) + 8 N G (half-transformed plane written)) '
+            'x occupied fraction {:.3f}'.format(occ)),
         'image_to_grid_rows': hbm_roofline(
             'image_to_grid_rows', 'rows_fwd_kernel<8192,256,16,16,2> (kib_gridfft.cu)',
             4.0 * N * N + 8.0 * N * G, 'fused_rows_fwd_dram_bytes_per_launch',
-            'algorithmic bytes = 4 N^2 (image read) + 8 N G (half-transformed plane written)'),
+            'algorithmic bytes = 4 N^2 (image read) + 8 N G (half-transformed plane written); '
+            'all-zero model rows are answered without a transform, hence frac > 1'),
         'image_to_grid_columns': hbm_roofline(
-            'image_to_grid_columns', 'columns_fwd_kernel + unfold_kernel (kib_gridfft.cu)',
-            8.0 * N * G + 8.0 * G * G, 'fused_columns_fwd_dram_bytes_per_launch',
-            'algorithmic bytes = 8 N G (read) + 8 G^2 (grid plane written)'),
+            'image_to_grid_columns', 'columns_fwd_cluster_kernel<8,1024,8> (kib_gridfft.cu)',
+            (8.0 * N * G + 8.0 * G * G) * occ, 'fused_columns_fwd_dram_bytes_per_launch',
+            'algorithmic bytes = (8 N G (read) + 8 G^2 (grid plane written)) x occupied '
+            'fraction {:.3f}'.format(occ)),
         'gridder': fp32_roofline(
             'grid', 'grid_stage_kernel<4> + grid_tma_kernel<float,4,7,1> (kib_grid.cu)',
             work['gridded_vis'], 'grid_dram_bytes_per_vis', 10 + 12 * POLS),
@@ -783,6 +812,9 @@ def run_gpu(args, ranks):
                            'downloaded on copy streams while the device images; one upload '
                            'and one download per step, the last download awaited inside the '
                            'timed region'},
+        'column_occupancy': {'mean': occ, 'per_w_slice': occupied,
+                             'note': 'fraction of the groups of 8 grid columns each W slice touches; '
+                                     'the grid <-> image transforms skip the others'},
         'step_stats': {k: (list(v) if isinstance(v, tuple) else
                            (float(v) if isinstance(v, (np.floating, float)) else v))
                        for k, v in stats.items()},

@@ -72,6 +72,27 @@ __device__ __forceinline__ Best<Real> block_best(Best<Real> v, Best<Real> *scrat
     return scratch[32];
 }
 
+// The same reduction with the result valid in thread 0 only and a single barrier.  Successive
+// calls must alternate between two scratch buffers (8 entries each, blocks of 256 threads): a
+// warp that writes buffer b for call n + 2 has passed the barrier of call n + 1, which warp 0
+// only reaches after it has read buffer b for call n.
+template <typename Real>
+__device__ __forceinline__ Best<Real> block_best_thread0(Best<Real> v, Best<Real> *scratch /* [8] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_best(v);
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        Best<Real> w;
+        w.value = -1;
+        w.key = INT_MAX;
+        if (lane < CLEAN_THREADS / 32) w = scratch[lane];
+        v = warp_best(w);
+    }
+    return v;
+}
+
 template <typename Real> __device__ __forceinline__ Real mul_rn_(Real a, Real b);
 template <> __device__ __forceinline__ float mul_rn_(float a, float b) { return __fmul_rn(a, b); }
 template <> __device__ __forceinline__ double mul_rn_(double a, double b) { return __dmul_rn(a, b); }
@@ -309,7 +330,7 @@ __device__ __forceinline__ CleanCycle clean_cycle_geometry(const CleanStepParams
 template <typename Real, int P, int MODE>
 __device__ __forceinline__ void clean_cell(const CleanStepParams &prm, const CleanCycle &g,
                                            const Real (&scale)[P], int cell_x, int cell_y,
-                                           Best<Real> *scratch)
+                                           Best<Real> (*scratch)[CLEAN_THREADS / 32], int &parity)
 {
     Real *const dirty = static_cast<Real *>(prm.dirty);
     const Real *const psf = static_cast<const Real *>(prm.psf);
@@ -325,30 +346,50 @@ __device__ __forceinline__ void clean_cell(const CleanStepParams &prm, const Cle
     best.key = INT_MAX;
     const bool x_in_patch = x >= g.cx0 && x < g.cx1;
     const bool x_in_tile = is_tile && x >= border && x < W - border;
+    // All loads of the thread's four rows are issued before the first store: a load of `dirty`
+    // may not pass an earlier store to `dirty`, so a loop of load / subtract / store per row
+    // pays one L2 round trip per row (four per cell) instead of one.
+    Real d[TILE / 8][P], psfv[TILE / 8][P];
+    bool in_patch[TILE / 8], in_tile[TILE / 8];
 #pragma unroll
     for (int k = 0; k < TILE / 8; k++) {
         const int y = ry0 + ly + 8 * k;
-        const bool in_patch = x_in_patch && y >= g.cy0 && y < g.cy1;
-        const bool in_tile = x_in_tile && y >= border && y < H - border;
-        if (in_patch || in_tile) {
+        in_patch[k] = x_in_patch && y >= g.cy0 && y < g.cy1;
+        in_tile[k] = x_in_tile && y >= border && y < H - border;
+        const long long addr = (long long) y * prm.row_stride + x;
+        if (in_patch[k]) {
+            const long long paddr = (long long) (y + g.psf_y0) * prm.psf_row_stride + x + g.psf_x0;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                d[k][p] = dirty[p * prm.pol_stride + addr];
+                psfv[k][p] = __ldg(psf + p * prm.psf_pol_stride + paddr);
+            }
+        } else if (in_tile[k]) {
+            const int np = MODE == KIB_CLEAN_I ? 1 : P;
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                if (p < np) d[k][p] = dirty[p * prm.pol_stride + addr];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TILE / 8; k++) {
+        const int y = ry0 + ly + 8 * k;
+        if (in_patch[k] || in_tile[k]) {
             const long long addr = (long long) y * prm.row_stride + x;
             Real pix[P];
-            if (in_patch) {
-                const long long paddr = (long long) (y + g.psf_y0) * prm.psf_row_stride + x + g.psf_x0;
+            if (in_patch[k]) {
 #pragma unroll
                 for (int p = 0; p < P; p++) {
-                    const Real d = dirty[p * prm.pol_stride + addr];
-                    const Real s = __ldg(psf + p * prm.psf_pol_stride + paddr);
-                    pix[p] = add_rn_(d, -mul_rn_(scale[p], s));
+                    pix[p] = add_rn_(d[k][p], -mul_rn_(scale[p], psfv[k][p]));
                     dirty[p * prm.pol_stride + addr] = pix[p];
                 }
             } else {
                 const int np = MODE == KIB_CLEAN_I ? 1 : P;
 #pragma unroll
                 for (int p = 0; p < P; p++)
-                    if (p < np) pix[p] = dirty[p * prm.pol_stride + addr];
+                    if (p < np) pix[p] = d[k][p];
             }
-            if (in_tile) {
+            if (in_tile[k]) {
                 const Real value = clean_metric<Real, MODE>(pix, P);
                 if (value > best.value) {
                     best.value = value;
@@ -358,7 +399,8 @@ __device__ __forceinline__ void clean_cell(const CleanStepParams &prm, const Cle
         }
     }
     if (is_tile) {
-        best = block_best(best, scratch);
+        best = block_best_thread0(best, scratch[parity]);
+        parity ^= 1;
         if (threadIdx.x == 0) {
             const long long idx = (long long) cell_y * prm.tile_stride + cell_x;
             static_cast<Real *>(prm.tile_max)[idx] = best.value;
@@ -464,9 +506,11 @@ clean_step_kernel(const CleanStepParams prm)
         scale[p] = mul_rn_((Real) prm.loop_gain, __ldcg(static_cast<Real *>(prm.peak_pixel) + p));
     // the launch grid covers the largest number of cells a patch can touch; blocks beyond this
     // cycle's cells have nothing to subtract
+    __shared__ Best<Real> cell_scratch[2][CLEAN_THREADS / 32];
+    int parity = 0;
     if ((int) blockIdx.x < g.cells_x && (int) blockIdx.y < g.cells_y)
         clean_cell<Real, P, MODE>(prm, g, scale, g.cell_x0 + blockIdx.x, g.cell_y0 + blockIdx.y,
-                                  scratch);
+                                  cell_scratch, parity);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
         clean_record<Real, P>(prm, g, scale, pv, done);
     // Last block to finish selects the next peak.
@@ -519,13 +563,15 @@ __device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
 }
 
 template <int P, int MODE>
-__global__ void __launch_bounds__(CLEAN_THREADS)
+__global__ void __launch_bounds__(CLEAN_THREADS, 4)
 clean_persistent_kernel(const CleanStepParams prm)
 {
     typedef float Real;
     __shared__ Best<Real> scratch[33];
     __shared__ int is_last;
     __shared__ unsigned s_peak[8];                       // y, x, value, pixel[0..3]
+    __shared__ Best<Real> cell_scratch[2][CLEAN_THREADS / 32];
+    int parity = 0;
     int *state = prm.state;
     uint4 *const packets = reinterpret_cast<uint4 *>(state + 4);
     const int nblocks = (int) gridDim.x;
@@ -570,7 +616,8 @@ clean_persistent_kernel(const CleanStepParams prm)
         const int cells = g.cells_x * g.cells_y;
         for (int cell = blockIdx.x; cell < cells; cell += nblocks) {
             const int cy = cell / g.cells_x, cx = cell - cy * g.cells_x;
-            clean_cell<Real, P, MODE>(prm, g, scale, g.cell_x0 + cx, g.cell_y0 + cy, scratch);
+            clean_cell<Real, P, MODE>(prm, g, scale, g.cell_x0 + cx, g.cell_y0 + cy, cell_scratch,
+                                      parity);
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) clean_record<Real, P>(prm, g, scale, pv, done);
         // ---- arrive; the last arrival finds the next peak and publishes it

@@ -346,12 +346,15 @@ class GridToImage(accel.OperationSequence):
         presence = None
         if occ is not None:
             # the row pass's view of the mask, made once per mask and image size
+            # (`generation` counts the times the owner refilled the mask in place)
             tables = occ.__dict__.setdefault('_row_presence', {})
-            presence = tables.get((n, size))
+            generation = getattr(occ, 'generation', 0)
+            presence, made_for = tables.get((n, size), (None, None))
             if presence is None:
                 presence = accel.DeviceArray(self.command_queue.context, (n // 16,), np.uint16)
+            if made_for != generation:
                 _lib.call('kib_row_presence', occ.ptr, size, n, presence.ptr, stream)
-                tables[(n, size)] = presence
+                tables[(n, size)] = (presence, generation)
         for pol in range(polarizations):
             mode = 0 if factors is None else (1 if pol == 0 else 2)
             grid_plane = (grid.ptr.value or 0) + pol * plane_bytes

@@ -119,7 +119,7 @@ class ResidentVisibilities:
         queue = self.command_queue
         keepalive = []
         self.h2d_bytes = 0
-        self.__dict__.pop('_occupancy', None)       # new records, new footprints
+        self.__dict__.pop('_occupancy_valid', None)     # new records, new footprints
         base = self.buffer.ptr.value or 0
         for records, offset in zip(slices, self.offsets):
             if len(records) == 0:
@@ -190,15 +190,24 @@ class ResidentVisibilities:
 
     def occupancy(self, queue, w_slice, kernel_width, grid_size):
         """Column occupancy of a W slice (:func:`.image.column_occupancy`): computed on the
-        device from the resident records the first time it is asked for, then kept."""
+        device from the resident records the first time it is asked for after an upload, then
+        kept.  The mask buffers themselves live as long as this object (allocating or freeing
+        device memory in the middle of a channel stalls the device)."""
         from . import image
         cache = self.__dict__.setdefault('_occupancy', {})
+        valid = self.__dict__.setdefault('_occupancy_valid', set())
         key = (w_slice, kernel_width, grid_size)
-        if key not in cache:
+        if key not in valid:
             base = (self.buffer.ptr.value or 0) + self.offsets[w_slice]
+            out = cache.get(key)
+            if out is not None:
+                out.zero(queue)
+                out.generation = getattr(out, 'generation', 0) + 1
             with profile_device(queue, 'column_occupancy'):
                 cache[key] = image.column_occupancy(queue, base, self.counts[w_slice],
-                                                    kernel_width, grid_size, self.record_bytes)
+                                                    kernel_width, grid_size, self.record_bytes,
+                                                    out=out)
+            valid.add(key)
         return cache[key]
 
     def feed(self, imager, w_slice, start, count, field, with_weights):
