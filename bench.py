@@ -644,13 +644,17 @@ def run_gpu(args, ranks):
         cur, nxt = e2e_bufs[k % 2], e2e_bufs[(k + 1) % 2]
         if read_done[(k + 1) % 2] is not None:      # the step that last read `nxt` must be over
             h2d_queue.enqueue_wait_for_events([read_done[(k + 1) % 2]])
-        nxt.upload(pinned_slices)
+        if not os.environ.get('KIB_E2E_NO_UPLOAD'):         # diagnostics only
+            nxt.upload(pinned_slices)
         queue.enqueue_wait_for_events([cur._uploaded])
         pipeline.process_channel(imager, cur, ip, gp, cp, wp, MAJOR, VIS_BLOCK,
                                  restore=restorer)
         read_done[k % 2] = queue.enqueue_marker()
-        e2e_state['stored'] = cube.store_device(ranks.rank, imager.buffer('dirty'), queue,
-                                                d2h_queue)
+        if os.environ.get('KIB_E2E_NO_STORE'):              # diagnostics only
+            e2e_state['stored'] = queue.enqueue_marker()
+        else:
+            e2e_state['stored'] = cube.store_device(ranks.rank, imager.buffer('dirty'), queue,
+                                                    d2h_queue)
         e2e_state['step'] = k + 1
 
     step_e2e()

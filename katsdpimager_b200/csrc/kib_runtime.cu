@@ -64,6 +64,72 @@ static const char *cufft_error_string(cufftResult r)
         }                                                                           \
     } while (0)
 
+// Small device-to-host reads (scalars, peaks, histograms: what the host waits for between the
+// stages of a channel) are written into the pinned destination by a kernel instead of going
+// through the copy engine: the engine serves its queue in order, so a read issued while the
+// previous channel's image (1 GB) is on its way out would wait for all of it -- 20 ms per
+// channel in bench.py's end-to-end leg.
+constexpr size_t SMALL_D2H_BYTES = 256 * 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+small_d2h_kernel(T *__restrict__ dst, size_t dst_row_pitch, size_t dst_plane_pitch,
+                 const T *__restrict__ src, size_t src_row_pitch, size_t src_plane_pitch,
+                 size_t width, size_t height, size_t depth)
+{
+    // pitches and width in units of T
+    const size_t total = width * height * depth;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t) gridDim.x * blockDim.x) {
+        const size_t x = i % width, r = i / width;
+        const size_t y = r % height, z = r / height;
+        dst[z * dst_plane_pitch + y * dst_row_pitch + x] = src[z * src_plane_pitch + y * src_row_pitch + x];
+    }
+}
+
+// Device-visible address of `host` if it is page-locked memory the device can write, else null.
+static void *mapped_pointer(const void *host)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+        (void) cudaGetLastError();
+        return nullptr;
+    }
+    return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+}
+
+// Returns 1 if the copy was not taken (too large, destination not mapped).
+static int small_d2h(void *dst, size_t dst_row_pitch, size_t dst_plane_pitch,
+                     const void *src, size_t src_row_pitch, size_t src_plane_pitch,
+                     size_t width_bytes, size_t height, size_t depth, cudaStream_t stream)
+{
+    const size_t total = width_bytes * height * depth;
+    if (total > SMALL_D2H_BYTES) return 1;
+    void *mapped = mapped_pointer(dst);
+    if (mapped == nullptr) return 1;
+    // whole rows of a few planes lie inside one pinned allocation; the last byte as a check
+    if (mapped_pointer(static_cast<const char *>(dst) + (depth - 1) * dst_plane_pitch
+                       + (height - 1) * dst_row_pitch + width_bytes - 1) == nullptr)
+        return 1;
+    const bool words = ((reinterpret_cast<size_t>(mapped) | reinterpret_cast<size_t>(src)
+                         | dst_row_pitch | dst_plane_pitch | src_row_pitch | src_plane_pitch
+                         | width_bytes) & 3) == 0;
+    const size_t elems = words ? total / 4 : total;
+    const unsigned blocks = (unsigned) ((elems + 255) / 256 > 64 ? 64 : (elems + 255) / 256);
+    if (words)
+        small_d2h_kernel<unsigned><<<blocks, 256, 0, stream>>>(
+            static_cast<unsigned *>(mapped), dst_row_pitch / 4, dst_plane_pitch / 4,
+            static_cast<const unsigned *>(src), src_row_pitch / 4, src_plane_pitch / 4,
+            width_bytes / 4, height, depth);
+    else
+        small_d2h_kernel<unsigned char><<<blocks, 256, 0, stream>>>(
+            static_cast<unsigned char *>(mapped), dst_row_pitch, dst_plane_pitch,
+            static_cast<const unsigned char *>(src), src_row_pitch, src_plane_pitch,
+            width_bytes, height, depth);
+    KIB_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace kib
 
 using namespace kib;
@@ -270,6 +336,8 @@ int kib_memcpy_h2d_async(void *dst, const void *src, size_t bytes, kib_stream_t 
 int kib_memcpy_d2h_async(void *dst, const void *src, size_t bytes, kib_stream_t stream)
 {
     if (bytes == 0) return 0;
+    const int rc = small_d2h(dst, bytes, bytes, src, bytes, bytes, bytes, 1, 1, as_stream(stream));
+    if (rc != 1) return rc;
     KIB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
     return 0;
 }
@@ -287,6 +355,11 @@ int kib_memcpy3d_async(void *dst, size_t dst_row_pitch, size_t dst_plane_pitch,
                        int kind, kib_stream_t stream)
 {
     if (width_bytes == 0 || height == 0 || depth == 0) return 0;
+    if (kind == 1) {
+        const int rc = small_d2h(dst, dst_row_pitch, dst_plane_pitch, src, src_row_pitch,
+                                 src_plane_pitch, width_bytes, height, depth, as_stream(stream));
+        if (rc != 1) return rc;
+    }
     cudaMemcpyKind k;
     switch (kind) {
     case 0: k = cudaMemcpyHostToDevice; break;

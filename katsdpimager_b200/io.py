@@ -180,6 +180,10 @@ def read_fits(filename):
     return header, data.astype(np.float32)
 
 
+#: bytes per piece of an overlapped device-to-host copy (see FitsCube.store_device)
+COPY_PIECE = 8 << 20
+
+
 class FitsCube:
     """A spectral cube (channels x polarizations x m x l) in one FITS file, shared between
     worker processes through the file mapping.
@@ -280,8 +284,14 @@ class FitsCube:
         if self._pinned is not None:
             if copy_queue is not None and copy_queue is not queue:
                 copy_queue.enqueue_wait_for_events([queue.enqueue_marker()])
-                _lib.call('kib_memcpy_d2h_async', self.data[channel].ctypes.data,
-                          self._staging.ptr, nbytes, copy_queue.stream)
+                # In pieces: the copy engine serves its streams piece by piece, so the small
+                # device-to-host reads of the next channel (PSF peak, noise estimate, CLEAN
+                # results) wait for one piece instead of the whole plane.
+                dst = self.data[channel].ctypes.data
+                src = self._staging.ptr.value or 0
+                for offset in range(0, nbytes, COPY_PIECE):
+                    _lib.call('kib_memcpy_d2h_async', dst + offset, src + offset,
+                              min(COPY_PIECE, nbytes - offset), copy_queue.stream)
                 self._stored = copy_queue.enqueue_marker()
                 return self._stored
             _lib.call('kib_memcpy_d2h_async', self.data[channel].ctypes.data, self._staging.ptr,

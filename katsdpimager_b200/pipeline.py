@@ -25,6 +25,10 @@ from . import _lib, accel, clean, weight
 from .profiling import profile_device
 
 
+#: bytes per host-to-device copy of an upload
+UPLOAD_PIECE = 16 << 20
+
+
 class ResidentVisibilities:
     """Preprocessed visibility records of one channel in HBM, W slices back to back.
 
@@ -133,7 +137,10 @@ class ResidentVisibilities:
                 pinned = accel.HostArray((nbytes,), np.uint8, context=queue.context)
                 pinned[:] = raw
                 raw = pinned
-            _lib.call('kib_memcpy_h2d_async', base + offset, raw.ctypes.data, nbytes, queue.stream)
+            # in pieces, so that small copies of other streams are not stuck behind a 280 MB one
+            for piece in range(0, nbytes, UPLOAD_PIECE):
+                _lib.call('kib_memcpy_h2d_async', base + offset + piece, raw.ctypes.data + piece,
+                          min(UPLOAD_PIECE, nbytes - piece), queue.stream)
             keepalive.append(raw)
             self.h2d_bytes += nbytes
         if self._uploaded is not None and self._keepalive:
