@@ -316,11 +316,48 @@ class GridToImage(accel.OperationSequence):
         #: caller promises that the grid is zero outside the occupied column groups; the fused
         #: transform then skips them (bit-identical image).
         self.occupancy = None
+        #: Keep the per-pixel factor plane (W rotation, n, taper: N x N complex, 0.5 GB at
+        #: 8192^2) of up to this many values of w: the W slices of a channel are transformed
+        #: once per pass (PSF, every major cycle) with the same factors, which the first
+        #: polarization of the first pass then computes and stores for all later launches.
+        #: 0 = one plane, recomputed by the first polarization of every call (round 1).
+        self.factor_cache_planes = 0
         self._factors = None
+        self._factor_cache = {}
         self._fold = None
 
     def set_w(self, w):
         self._layer_to_image.set_w(w)
+
+    def clear_factor_cache(self):
+        """Forget the cached factor planes (a new channel: new pixel size, new slice centres).
+        The buffers are kept for reuse."""
+        self._factor_pool = getattr(self, '_factor_pool', []) + list(self._factor_cache.values())
+        self._factor_cache = {}
+
+    def _factor_plane(self, n, dtype, key):
+        """(plane, already computed?) for the factors identified by `key`."""
+        context = self.command_queue.context
+        if self.factor_cache_planes <= 0:
+            if self._factors is None or self._factors.shape != (n, n):
+                self._factors = accel.DeviceArray(context, (n, n), dtype)
+            return self._factors, False
+        plane = self._factor_cache.get(key)
+        if plane is not None:
+            return plane, True
+        pool = getattr(self, '_factor_pool', [])
+        while len(self._factor_cache) >= self.factor_cache_planes:
+            pool.append(self._factor_cache.pop(next(iter(self._factor_cache))))   # oldest first
+        plane = None
+        while pool and plane is None:
+            candidate = pool.pop()
+            if candidate.shape == (n, n) and candidate.dtype == dtype:
+                plane = candidate
+        self._factor_pool = pool
+        if plane is None:
+            plane = accel.DeviceArray(context, (n, n), dtype)
+        self._factor_cache[key] = plane
+        return plane, False
 
     def _run_fused(self, grid, layer, polarizations, size, plane_bytes):
         """Pruned transform with the layer_to_image arithmetic fused in
@@ -333,12 +370,14 @@ class GridToImage(accel.OperationSequence):
         stream = self.command_queue.stream
         n = layer.shape[1]
         factors = None
-        if polarizations > 1:
+        have_factors = False
+        if polarizations > 1 or self.factor_cache_planes > 0:
             # the W rotation / n / taper factor of every pixel is computed for the first
-            # polarization, kept, and reused by the others
-            if self._factors is None or self._factors.shape != (n, n):
-                self._factors = accel.DeviceArray(self.command_queue.context, (n, n), grid.dtype)
-            factors = self._factors.ptr
+            # polarization, kept, and reused by the others (and by later passes over the same
+            # W slice when the cache is on)
+            key = (float(op.w), float(op.lm_scale), float(op.lm_bias), kernel1d.ptr.value, n)
+            plane, have_factors = self._factor_plane(n, grid.dtype, key)
+            factors = plane.ptr
         fold_bytes = _lib.grid_to_image_fold_bytes(n, size)
         if self._fold is None or self._fold.shape[0] < fold_bytes:
             self._fold = accel.DeviceArray(self.command_queue.context, (fold_bytes,), np.uint8)
@@ -356,7 +395,7 @@ class GridToImage(accel.OperationSequence):
                 _lib.call('kib_row_presence', occ.ptr, size, n, presence.ptr, stream)
                 tables[(n, size)] = (presence, generation)
         for pol in range(polarizations):
-            mode = 0 if factors is None else (1 if pol == 0 else 2)
+            mode = 0 if factors is None else (1 if pol == 0 and not have_factors else 2)
             grid_plane = (grid.ptr.value or 0) + pol * plane_bytes
             image_ptr = (image.ptr.value or 0) + pol * image_plane
             if occ is not None:

@@ -481,6 +481,14 @@ class Imaging(accel.OperationSequence):
     def kernel_width(self):
         return self.template.fixed_grid_parameters.kernel_width
 
+    def new_channel(self, w_slices=0):
+        """Tell the imager that the next calls image another channel with `w_slices` W slices
+        (not in the reference, which builds a new Imaging per channel): per-slice factor planes
+        of the grid -> image transform are kept across the passes over this channel
+        (:attr:`.image.GridToImage.factor_cache_planes`) and dropped here."""
+        self._grid_to_image.clear_factor_cache()
+        self._grid_to_image.factor_cache_planes = int(w_slices)
+
     @profile_function()
     def model_to_predict(self):
         if self.template.fixed_grid_parameters.degrid:

@@ -329,6 +329,10 @@ def process_channel(imager, vis, image_parameters, grid_parameters, clean_parame
     if len(vis) == 0:
         stats['skipped'] = 'no data'
         return stats
+    if hasattr(imager, 'new_channel'):
+        # factor planes of the non-empty W slices are computed in the first pass and reused by
+        # the others (0.5 GB each at 8192^2; never across channels)
+        imager.new_channel(sum(1 for w in range(vis.num_w_slices) if vis.len(w)))
     imager.clear_model()
     weights_noise, normalized_noise = make_weights(imager, vis, weight_parameters.weight_type,
                                                    vis_block)

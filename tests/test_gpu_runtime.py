@@ -57,6 +57,47 @@ def test_regions(gpu):
     np.testing.assert_array_equal(vis.get(queue), expected)
 
 
+def test_small_reads_into_pinned_memory(gpu):
+    """Device-to-host reads of up to 256 KB into page-locked memory are written by a kernel
+    (kib_runtime.cu: small_d2h) instead of the copy engine: contiguous and strided, word- and
+    byte-aligned, into pinned and into pageable destinations (the latter take the copy engine),
+    and just around the size limit."""
+    context, queue = gpu
+    rs = np.random.RandomState(3)
+    # contiguous, several sizes around the limit and not multiples of 4 bytes
+    for nbytes in (1, 3, 4, 1000, 4099, 256 * 1024, 256 * 1024 + 4):
+        ref = rs.randint(0, 256, nbytes).astype(np.uint8)
+        dev = accel.DeviceArray(context, (nbytes,), np.uint8)
+        dev.set(queue, ref)
+        pinned = accel.HostArray((nbytes,), np.uint8, context=context)
+        pinned[:] = 0
+        dev.get(queue, pinned)
+        np.testing.assert_array_equal(np.asarray(pinned), ref)
+        pageable = np.zeros(nbytes, np.uint8)
+        dev.get(queue, pageable)
+        np.testing.assert_array_equal(pageable, ref)
+    # strided on both sides (the PSF-peak read of pipeline.process_channel is one of these)
+    dev = accel.DeviceArray(context, (4, 50, 60), np.float32, (4, 56, 64))
+    ref = rs.uniform(size=dev.shape).astype(np.float32)
+    dev.set(queue, ref)
+    peak = accel.HostArray((4,), np.float32, context=context)
+    dev.get_region(queue, peak, np.s_[:, 25, 30], np.s_[:])
+    np.testing.assert_array_equal(np.asarray(peak), ref[:, 25, 30])
+    out = accel.HostArray((4, 9, 16), np.float32, context=context)
+    out[:] = -1
+    dev.get_region(queue, out, np.s_[1:3, 7:13, 5:12], np.s_[2:4, 1:7, 3:10])
+    expected = np.full((4, 9, 16), -1, np.float32)
+    expected[2:4, 1:7, 3:10] = ref[1:3, 7:13, 5:12]
+    np.testing.assert_array_equal(np.asarray(out), expected)
+    # int16 columns: byte-granular path
+    vis = accel.DeviceArray(context, (100, 3), np.int16)
+    host = rs.randint(-100, 100, (100, 3)).astype(np.int16)
+    vis.set(queue, host)
+    col = accel.HostArray((100, 1), np.int16, context=context)
+    vis.get_region(queue, col, np.s_[:, 1:2], np.s_[:, :])
+    np.testing.assert_array_equal(np.asarray(col), host[:, 1:2])
+
+
 def test_events(gpu):
     context, queue = gpu
     dev = accel.DeviceArray(context, (1 << 22,), np.float32)
