@@ -275,6 +275,12 @@ int kib_grid_to_image_columns_occ(void *scratch, int scratch_row_stride, int siz
                                   const void *grid_plane, int grid_row_stride, int grid_size,
                                   void *fold_scratch, const uint32_t *occupancy, int dtype,
                                   kib_stream_t stream);
+/* kib_clear_columns zeroes the occupied column groups of a float32 grid (all polarizations) and
+ * leaves the others alone: enough for a grid that is then filled by kib_grid with the same
+ * visibilities and read through the *_occ transforms (replaces the whole-buffer memset of
+ * Imaging.clear_grid, reference imaging.py:253-255). */
+int kib_clear_columns(void *grid, int grid_row_stride, int64_t grid_pol_stride, int grid_size,
+                      int num_pols, const uint32_t *occupancy, int dtype, kib_stream_t stream);
 /* The row pass wants the mask per first-stage butterfly: kib_row_presence turns `occupancy` into
  * `presence` (size / 16 uint16, owned by the caller) for an image of size^2 pixels;
  * kib_grid_to_image_rows_occ takes that table. */

@@ -329,6 +329,16 @@ class GridToImage(accel.OperationSequence):
     def set_w(self, w):
         self._layer_to_image.set_w(w)
 
+    @property
+    def uses_occupancy(self):
+        """Whether :attr:`occupancy` is honoured (the fused transform is available for the bound
+        shapes).  If not, every column of the grid is read and must be cleared."""
+        grid = self.buffer('grid')
+        layer = self.buffer('layer')
+        if not self.fused or grid is None or layer is None:
+            return False
+        return bool(_lib.grid_to_image_supported(layer.shape[1], grid.shape[-1], grid.dtype))
+
     def clear_factor_cache(self):
         """Forget the cached factor planes (a new channel: new pixel size, new slice centres).
         The buffers are kept for reuse."""

@@ -401,10 +401,19 @@ class Imaging(accel.OperationSequence):
     double_buffer_grid = True
 
     @profile_function()
-    def clear_grid(self):
+    def clear_grid(self, occupancy=None, next_occupancy=None):
+        """Zero the grid (reference imaging.py:253-255).
+
+        Not in the reference: with `occupancy` (the column occupancy of everything that will be
+        gridded before the next clear, :func:`.image.column_occupancy`) only those columns are
+        guaranteed to be zero afterwards -- the caller reads the grid through
+        ``grid_to_image(w, occupancy=...)`` only.  `next_occupancy` is the same for the clear
+        after this one, which the second grid buffer receives ahead of time."""
         current = self.buffer('grid')
+        if occupancy is not None and not self._grid_to_image.uses_occupancy:
+            occupancy = next_occupancy = None       # the dense transform reads every column
         if not self.double_buffer_grid or current is None:
-            self._zero('grid')
+            self._clear_grid_buffer(self.command_queue, current, occupancy)
             return
         queue = self.command_queue
         spare = getattr(self, '_grid_spare', None)
@@ -416,9 +425,9 @@ class Imaging(accel.OperationSequence):
             self._side_queue = queue.context.create_command_queue()
             self._grid_spare = accel.DeviceArray(queue.context, current.shape, current.dtype,
                                                  current.padded_shape)
-            self._zero('grid')
-            with profile_device(self._side_queue, 'clear_grid'):
-                self._grid_spare.zero(self._side_queue)
+            self._clear_grid_buffer(queue, current, occupancy)
+            self._spare_cleared_for = self._clear_grid_buffer(self._side_queue, self._grid_spare,
+                                                              next_occupancy)
             self._spare_zeroed = self._side_queue.enqueue_marker()
             return
         # everything enqueued so far (the transform of the previous slice) is done with
@@ -426,11 +435,36 @@ class Imaging(accel.OperationSequence):
         done = queue.enqueue_marker()
         queue.enqueue_wait_for_events([self._spare_zeroed])
         self.bind(grid=spare)
+        if not self._clear_covers(self._spare_cleared_for, occupancy):
+            # the spare was prepared for other columns (first slice of a pass, new channel)
+            self._clear_grid_buffer(queue, spare, occupancy)
         self._grid_spare = current
         self._side_queue.enqueue_wait_for_events([done])
-        with profile_device(self._side_queue, 'clear_grid'):
-            current.zero(self._side_queue)
+        self._spare_cleared_for = self._clear_grid_buffer(self._side_queue, current,
+                                                          next_occupancy)
         self._spare_zeroed = self._side_queue.enqueue_marker()
+
+    @staticmethod
+    def _clear_covers(cleared_for, occupancy):
+        """Does a clear made for `cleared_for` (None = everything) leave the columns of
+        `occupancy` zero?"""
+        if cleared_for is None:
+            return True
+        if occupancy is None:
+            return False
+        return cleared_for[0] is occupancy and cleared_for[1] == getattr(occupancy, 'generation', 0)
+
+    def _clear_grid_buffer(self, queue, buffer, occupancy):
+        """Zero `buffer` (whole, or the column groups of `occupancy`) on `queue`; returns what
+        :meth:`_clear_covers` compares."""
+        with profile_device(queue, 'clear_grid'):
+            if occupancy is None or buffer.dtype != np.complex64:
+                buffer.zero(queue)
+                return None
+            _lib.call('kib_clear_columns', buffer.ptr, buffer.padded_shape[2],
+                      buffer.padded_shape[1] * buffer.padded_shape[2], buffer.shape[2],
+                      buffer.shape[0], occupancy.ptr, _lib.dtype_code(buffer.dtype), queue.stream)
+        return (occupancy, getattr(occupancy, 'generation', 0))     # keeps the mask alive
 
     @profile_function()
     def clear_dirty(self):
@@ -488,6 +522,10 @@ class Imaging(accel.OperationSequence):
         (:attr:`.image.GridToImage.factor_cache_planes`) and dropped here."""
         self._grid_to_image.clear_factor_cache()
         self._grid_to_image.factor_cache_planes = int(w_slices)
+        if getattr(self, '_spare_zeroed', None) is not None:
+            # the look-ahead clear of the second grid buffer reads an occupancy mask that the
+            # new channel may be about to refill in place
+            self.command_queue.enqueue_wait_for_events([self._spare_zeroed])
 
     @profile_function()
     def model_to_predict(self):

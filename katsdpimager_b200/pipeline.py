@@ -278,21 +278,28 @@ def make_dirty(imager, vis, field, mid_w, vis_block, degrid, full_cycle=False,
     imager.clear_dirty()
     if full_cycle and not degrid:
         imager.model_to_predict()
-    for w_slice in range(vis.num_w_slices):
-        if vis.len(w_slice) == 0:
-            continue
-        # which columns of the grid this slice touches (resident records only): the transforms
-        # skip the others -- same images, see image.column_occupancy
-        occupancy = None
-        if use_occupancy and hasattr(vis, 'occupancy') and hasattr(imager, 'kernel_width'):
-            occupancy = vis.occupancy(imager.command_queue, w_slice, imager.kernel_width,
-                                      imager.buffer('grid').shape[-1])
+    # which columns of the grid each slice touches (resident records only): the clears and the
+    # transforms skip the others -- same images, see image.column_occupancy
+    w_slices = [w for w in range(vis.num_w_slices) if vis.len(w)]
+    masks = {}
+    if use_occupancy and hasattr(vis, 'occupancy') and hasattr(imager, 'kernel_width'):
+        for w_slice in w_slices:
+            masks[w_slice] = vis.occupancy(imager.command_queue, w_slice, imager.kernel_width,
+                                           imager.buffer('grid').shape[-1])
+    for i, w_slice in enumerate(w_slices):
+        occupancy = masks.get(w_slice)
         if full_cycle and degrid:
             if occupancy is not None:
                 imager.model_to_grid(mid_w[w_slice], occupancy=occupancy)
             else:
                 imager.model_to_grid(mid_w[w_slice])
-        imager.clear_grid()
+        if occupancy is not None:
+            # the grid cleared ahead of time for the next clear: the next slice, or the first
+            # slice of the next pass
+            imager.clear_grid(occupancy=occupancy,
+                              next_occupancy=masks[w_slices[(i + 1) % len(w_slices)]])
+        else:
+            imager.clear_grid()
         for start, count in vis.chunks(w_slice, vis_block):
             vis.feed(imager, w_slice, start, count, field, full_cycle)
             if full_cycle:

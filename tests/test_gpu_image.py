@@ -612,3 +612,30 @@ def test_image_to_grid_occupancy(gpu, pixels, grid_size, sparse_model):
     assert (untouched | computed).all()
     assert untouched.sum() > 0.4 * rest.shape[2]
     assert np.abs(dense).max() > 0
+
+
+def test_clear_columns(gpu):
+    """kib_clear_columns zeroes exactly the occupied groups of 8 columns, in every
+    polarization, also with a padded grid and a last group that is cut by the grid edge."""
+    context, queue = gpu
+    from katsdpimager_b200 import _lib
+    rs = RandomState(7)
+    for grid_size, padded in ((1230, 1232), (500, 500)):
+        pols = 3
+        groups = (grid_size + 7) // 8
+        occupied = sorted(set(rs.randint(0, groups, groups // 2)) | {groups - 1})
+        keep = np.zeros(grid_size, bool)
+        for g in occupied:
+            keep[8 * g:8 * g + 8] = True
+        dev = accel.DeviceArray(context, (pols, grid_size, grid_size), np.complex64,
+                                (pols, grid_size + 3, padded))
+        ref = rs.complex_normal(0.0j, 1.0, dev.shape).astype(np.complex64)
+        dev.set(queue, ref)
+        occ = accel.DeviceArray(context, (image.occupancy_words(grid_size),), np.uint32)
+        occ.set(queue, _occupancy_mask(occupied, grid_size))
+        _lib.call('kib_clear_columns', dev.ptr, dev.padded_shape[2],
+                  dev.padded_shape[1] * dev.padded_shape[2], grid_size, pols, occ.ptr,
+                  _lib.dtype_code(dev.dtype), queue.stream)
+        out = dev.get(queue)
+        assert not out[:, :, keep].any()
+        np.testing.assert_array_equal(out[:, :, ~keep], ref[:, :, ~keep])

@@ -267,3 +267,46 @@ def test_pipeline_resident_matches_host_chunks(gpu, degrid):
     assert np.sqrt(np.mean((img0 - img1) ** 2)) <= 1e-5 * peak
     assert np.abs(img0 - img1).max() <= 1e-3 * peak
     assert np.count_nonzero(model0) > 0
+
+
+def test_pipeline_occupancy_matches_dense(gpu):
+    """pipeline.process_channel at a size the fused transform covers (2048^2): with the column
+    occupancy of every W slice (clears, grid -> image and image -> grid restricted to the
+    occupied column groups, factor planes cached across the passes) and without it (whole grids
+    cleared and transformed) -- same CLEAN history, images equal to the rounding of the
+    gridder's atomics."""
+    from katsdpimager_b200 import imaging, pipeline, weight
+    context, queue = gpu
+    fx = cases.imaging_case(pixels=2048, degrid=True)
+    ip, gp, cp = fx['image_parameters'], fx['grid_parameters'], fx['clean_parameters']
+    wp = prm.WeightParameters(weight.WeightType.ROBUST, 0.0)
+    slices = [fx['reader']._data[0][w] for w in range(gp.w_slices)]
+    template = imaging.ImagingTemplate(context, fx['array_parameters'], ip.fixed, wp, gp.fixed, cp)
+    results = []
+    for use_occupancy in (True, False):
+        imager = template.instantiate(queue, ip, gp, fx['vis_block'], 0, 3)
+        imager.ensure_all_bound()
+        assert imager._grid_to_image.uses_occupancy
+        # poison both grids: only what a pass clears may be relied upon
+        poison = np.full(imager.buffer('grid').shape, np.nan, np.complex64)
+        imager.buffer('grid').set(queue, poison)
+        imager.buffer('degrid').set(queue, poison)
+        vis = pipeline.ResidentVisibilities(queue, slices, len(ip.fixed.polarizations))
+        out = imager.buffer('dirty').empty_like()
+        stats = pipeline.process_channel(imager, vis, ip, gp, cp, wp, 3, fx['vis_block'], out=out,
+                                         use_occupancy=use_occupancy)
+        queue.finish()
+        results.append((stats, np.array(out), imager.get_buffer('model'),
+                        dict(imager._model_components)))
+        del imager
+    (s0, img0, model0, comp0), (s1, img1, model1, comp1) = results
+    assert np.isfinite(img0).all() and np.isfinite(img1).all()
+    assert s0['passes'] == 4 and s0['minor'] > 10
+    for key in ('passes', 'major', 'minor', 'psf_patch_size', 'compressed_vis'):
+        assert s0[key] == s1[key], key
+    np.testing.assert_allclose(s0['noise'], s1['noise'], rtol=1e-4)
+    assert sorted(comp0) == sorted(comp1)
+    peak = np.abs(img1).max()
+    assert np.abs(model0 - model1).max() <= 1e-5 * np.abs(model1).max()
+    assert np.sqrt(np.mean((img0 - img1) ** 2)) <= 1e-5 * peak
+    assert np.abs(img0 - img1).max() <= 1e-3 * peak
