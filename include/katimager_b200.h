@@ -251,6 +251,13 @@ int kib_image_to_grid_rows_sparse(void *scratch, int scratch_row_stride, int gri
                                   const void *image_plane, int image_row_stride,
                                   const void *kernel1d, double lm_scale, double lm_bias, double w,
                                   int32_t *row_info, int dtype, kib_stream_t stream);
+/* The same with a row_info that an earlier kib_image_to_grid_rows_sparse call filled for the
+ * same, unchanged image plane (the model is transformed once per W slice between two batches of
+ * CLEAN cycles: one classification pass over the plane instead of one per slice). */
+int kib_image_to_grid_rows_classified(void *scratch, int scratch_row_stride, int grid_size,
+                                      int size, const void *image_plane, int image_row_stride,
+                                      const void *kernel1d, double lm_scale, double lm_bias,
+                                      double w, int32_t *row_info, int dtype, kib_stream_t stream);
 int kib_image_to_grid_columns_sparse(void *grid_plane, int grid_row_stride, int grid_size,
                                      const void *scratch, int scratch_row_stride, int size,
                                      const int32_t *row_info, int dtype, kib_stream_t stream);

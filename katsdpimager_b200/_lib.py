@@ -79,6 +79,7 @@ SIGNATURES = {
     'kib_image_to_grid_columns': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_image_to_grid_sparse_supported': [_i, _i, _i],
     'kib_image_to_grid_rows_sparse': [_vp, _i, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _vp],
+    'kib_image_to_grid_rows_classified': [_vp, _i, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _vp],
     'kib_image_to_grid_columns_sparse': [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     'kib_grid_to_image_rows': [_vp, _i, _vp, _i, _i, _i, _vp, _d, _d, _d, _vp, _i, _i, _vp],
     'kib_column_occupancy': [_vp, c_int64, c_int64, _i, _i, _vp, _vp],
@@ -170,7 +171,7 @@ _ONE_KERNEL = frozenset([
     'kib_density_weights', 'kib_fill', 'kib_fits_plane', 'kib_fourier_beam', 'kib_predict', 'kib_fp32_peak_kernel',
     'kib_unpack_records', 'kib_grid_to_image_rows', 'kib_image_to_grid_rows',
     'kib_grid_to_image_rows_occ', 'kib_column_occupancy', 'kib_row_presence',
-    'kib_clear_columns'])
+    'kib_clear_columns', 'kib_image_to_grid_rows_classified'])
 
 #: number of hand-written kernels launched through this module (cuFFT and memset/memcpy
 #: are not counted); bench.py reports the difference over its timed region

@@ -783,17 +783,37 @@ abs_histogram_window_kernel(const float *__restrict__ image, int row_stride, lon
     __syncthreads();
     const int rows = inner_h * P;
     unsigned count_below = 0;
+    auto tally = [&](float value) {
+        const unsigned bits = __float_as_uint(fabsf(value));
+        const unsigned rel = (bits >> prefix_shift) - first_prefix;     // wraps when smaller
+        if (rel < window)
+            atomicAdd(&local[rel * bins + ((bits >> shift) & mask)], 1u);
+        else
+            count_below += (bits >> prefix_shift) < first_prefix;
+    };
+    // 16-byte loads, two per thread in flight, when every row segment is aligned (the pass is
+    // latency-bound with 4-byte loads: 41 % of the DRAM bandwidth at full occupancy)
+    const bool vec = ((reinterpret_cast<size_t>(image) | (size_t) border * 4 | (size_t) row_stride * 4
+                       | (size_t) pol_stride * 4) & 15) == 0 && (inner_w & 3) == 0;
     for (int r = blockIdx.x; r < rows; r += gridDim.x) {
         const int p = r / inner_h, y = r - p * inner_h;
         const float *row = image + p * pol_stride + (long long) (y + border) * row_stride + border;
+        if (vec) {
+            const float4 *row4 = reinterpret_cast<const float4 *>(row);
+            const int n4 = inner_w >> 2;
+            int x = threadIdx.x;
+            for (; x + 256 < n4; x += 512) {
+                const float4 a = __ldg(row4 + x), b = __ldg(row4 + x + 256);
+                tally(a.x); tally(a.y); tally(a.z); tally(a.w);
+                tally(b.x); tally(b.y); tally(b.z); tally(b.w);
+            }
+            if (x < n4) {
+                const float4 a = __ldg(row4 + x);
+                tally(a.x); tally(a.y); tally(a.z); tally(a.w);
+            }
+        } else {
 #pragma unroll 4
-        for (int x = threadIdx.x; x < inner_w; x += 256) {
-            const unsigned bits = __float_as_uint(fabsf(__ldg(row + x)));
-            const unsigned rel = (bits >> prefix_shift) - first_prefix;     // wraps when smaller
-            if (rel < window)
-                atomicAdd(&local[rel * bins + ((bits >> shift) & mask)], 1u);
-            else
-                count_below += (bits >> prefix_shift) < first_prefix;
+            for (int x = threadIdx.x; x < inner_w; x += 256) tally(__ldg(row + x));
         }
     }
 #pragma unroll

@@ -474,6 +474,12 @@ class ImageToGrid(accel.OperationSequence):
         #: degridded from the grid, or None.  When set, only the occupied column groups of the
         #: grid are computed; the others keep whatever they held.
         self.occupancy = None
+        #: The caller's promise that the image (the CLEAN model) has not changed since the
+        #: previous call of this operation: the sparse route then reuses its classification of
+        #: the rows instead of reading the whole plane again (the model is transformed once per
+        #: W slice between two batches of CLEAN cycles).
+        self.image_unchanged = False
+        self._classified = None
         self._factors = None
         self._fold = None
         self._row_info = None
@@ -495,24 +501,32 @@ class ImageToGrid(accel.OperationSequence):
         if self.sparse_model and _lib.load().kib_image_to_grid_sparse_supported(n, size, dtype):
             # only rows with a non-zero pixel are transformed; the column pass never reads the
             # others (taken as zero)
-            if self._row_info is None or self._row_info.shape[0] < 2 * n + 1:
-                self._row_info = accel.DeviceArray(context, (2 * n + 1,), np.int32)
+            words = 2 * n + 1
+            if self._row_info is None or self._row_info.shape[0] < polarizations * words:
+                self._row_info = accel.DeviceArray(context, (polarizations * words,), np.int32)
+                self._classified = None
+            state = (image.ptr.value, n, polarizations)
+            reuse = bool(self.image_unchanged) and self._classified == state
+            self._classified = state
             for pol in range(polarizations):
+                row_info = (self._row_info.ptr.value or 0) + pol * words * 4
                 with profile_device(self.command_queue, 'image_to_grid_rows'):
-                    _lib.call('kib_image_to_grid_rows_sparse', layer.ptr, layer.padded_shape[1],
+                    _lib.call('kib_image_to_grid_rows_classified' if reuse
+                              else 'kib_image_to_grid_rows_sparse', layer.ptr,
+                              layer.padded_shape[1],
                               size, n, (image.ptr.value or 0) + pol * image_plane,
                               image.padded_shape[2], kernel1d.ptr, float(op.lm_scale),
-                              float(op.lm_bias), float(op.w), self._row_info.ptr, dtype, stream)
+                              float(op.lm_bias), float(op.w), row_info, dtype, stream)
                 with profile_device(self.command_queue, 'image_to_grid_columns'):
                     if occ is not None:
                         _lib.call('kib_image_to_grid_columns_occ',
                                   (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2],
                                   size, layer.ptr, layer.padded_shape[1], n, None,
-                                  self._row_info.ptr, occ.ptr, dtype, stream)
+                                  row_info, occ.ptr, dtype, stream)
                     else:
                         _lib.call('kib_image_to_grid_columns_sparse',
                                   (grid.ptr.value or 0) + pol * plane_bytes, grid.padded_shape[2],
-                                  size, layer.ptr, layer.padded_shape[1], n, self._row_info.ptr,
+                                  size, layer.ptr, layer.padded_shape[1], n, row_info,
                                   dtype, stream)
             return
         factors = None

@@ -502,13 +502,16 @@ class Imaging(accel.OperationSequence):
         self._grid_to_image()
 
     @profile_function()
-    def model_to_grid(self, w, occupancy=None):
+    def model_to_grid(self, w, occupancy=None, model_unchanged=False):
         """`occupancy` (not in the reference): column occupancy of the visibilities that will be
-        predicted from the grid; the other columns of the grid are not computed."""
+        predicted from the grid; the other columns of the grid are not computed.
+        `model_unchanged` (not in the reference): the model is what it was at the previous call
+        (another W slice of the same pass), so its empty rows need not be looked for again."""
         if self._image_to_grid is None:
             raise RuntimeError('Can only use model_to_grid with degridding')
         self._image_to_grid.set_w(w)
         self._image_to_grid.occupancy = occupancy
+        self._image_to_grid.image_unchanged = bool(model_unchanged)
         self._image_to_grid()
 
     @property

@@ -290,7 +290,8 @@ def make_dirty(imager, vis, field, mid_w, vis_block, degrid, full_cycle=False,
         occupancy = masks.get(w_slice)
         if full_cycle and degrid:
             if occupancy is not None:
-                imager.model_to_grid(mid_w[w_slice], occupancy=occupancy)
+                # (the model only changes between passes)
+                imager.model_to_grid(mid_w[w_slice], occupancy=occupancy, model_unchanged=i > 0)
             else:
                 imager.model_to_grid(mid_w[w_slice])
         if occupancy is not None:
