@@ -192,6 +192,12 @@ int kib_layer_to_image(void *image_plane, int image_row_stride,
  *                              does not depend on the polarization: factor_mode 1 also
  *                              stores it in `factors` (size x size complex, row stride
  *                              size), 2 loads it from there, 0 ignores `factors`.
+ *                              factor_mode 3 / 4: as 1 / 2 when lm_bias = -size / 2 *
+ *                              lm_scale and kernel1d[i] = kernel1d[size - i] (what the
+ *                              reference's Imaging sets up, imaging.py:90-91, grid.py:404):
+ *                              the factor is then symmetric about the image centre and
+ *                              `factors` holds one quadrant, (size / 2 + 1)^2 complex
+ *                              values at [|y - size/2|][|x - size/2|].
  * kib_grid_to_image runs both (factor_mode 0).  The reference's layer buffer is large
  * enough as scratch.  Single precision and size in {2048, 4096, 8192, 16384} only;
  * kib_grid_to_image_supported returns 1 for supported combinations and 0 otherwise

@@ -322,6 +322,11 @@ class GridToImage(accel.OperationSequence):
         #: polarization of the first pass then computes and stores for all later launches.
         #: 0 = one plane, recomputed by the first polarization of every call (round 1).
         self.factor_cache_planes = 0
+        #: The caller's promise that lm_bias = -N / 2 * lm_scale and that kernel1d is symmetric
+        #: (kernel1d[i] == kernel1d[N - i]), as for the reference's taper: the factor plane is
+        #: then symmetric about the image centre and only one quadrant is kept (a quarter of
+        #: the bytes every launch has to read).
+        self.symmetric_factors = False
         self._factors = None
         self._factor_cache = {}
         self._fold = None
@@ -346,7 +351,8 @@ class GridToImage(accel.OperationSequence):
         self._factor_cache = {}
 
     def _factor_plane(self, n, dtype, key):
-        """(plane, already computed?) for the factors identified by `key`."""
+        """(plane, already computed?) for the factors identified by `key`; `n` is the side of
+        the table (the image's, or half of it + 1 for symmetric factors)."""
         context = self.command_queue.context
         if self.factor_cache_planes <= 0:
             if self._factors is None or self._factors.shape != (n, n):
@@ -381,12 +387,16 @@ class GridToImage(accel.OperationSequence):
         n = layer.shape[1]
         factors = None
         have_factors = False
+        symmetric = False
         if polarizations > 1 or self.factor_cache_planes > 0:
             # the W rotation / n / taper factor of every pixel is computed for the first
             # polarization, kept, and reused by the others (and by later passes over the same
             # W slice when the cache is on)
-            key = (float(op.w), float(op.lm_scale), float(op.lm_bias), kernel1d.ptr.value, n)
-            plane, have_factors = self._factor_plane(n, grid.dtype, key)
+            symmetric = bool(self.symmetric_factors) and abs(
+                float(op.lm_bias) + 0.5 * n * float(op.lm_scale)) <= 1e-6 * abs(float(op.lm_scale))
+            side = n // 2 + 1 if symmetric else n
+            key = (float(op.w), float(op.lm_scale), float(op.lm_bias), kernel1d.ptr.value, side)
+            plane, have_factors = self._factor_plane(side, grid.dtype, key)
             factors = plane.ptr
         fold_bytes = _lib.grid_to_image_fold_bytes(n, size)
         if self._fold is None or self._fold.shape[0] < fold_bytes:
@@ -406,6 +416,8 @@ class GridToImage(accel.OperationSequence):
                 tables[(n, size)] = (presence, generation)
         for pol in range(polarizations):
             mode = 0 if factors is None else (1 if pol == 0 and not have_factors else 2)
+            if mode and symmetric:
+                mode += 2                   # quadrant table
             grid_plane = (grid.ptr.value or 0) + pol * plane_bytes
             image_ptr = (image.ptr.value or 0) + pol * image_plane
             if occ is not None:

@@ -221,6 +221,9 @@ class Imaging(accel.OperationSequence):
         self._weights.robustness = template.weight_parameters.robustness
         self._grid_to_image = template.grid_image.instantiate_grid_to_image(
             command_queue, grid_shape, lm_scale, lm_bias, fft_plan, allocator)
+        # lm_bias = -pixels / 2 * lm_scale above and the taper of grid.ConvolutionKernel is an
+        # even function sampled symmetrically: one quadrant of the factor plane is enough
+        self._grid_to_image.symmetric_factors = pixels % 2 == 0
         self._psf_patch = instantiate(template.psf_patch, image_shape)
         self._noise_est = instantiate(template.noise_est, image_shape,
                                       template.clean_parameters.border)
