@@ -222,8 +222,13 @@ class Imaging(accel.OperationSequence):
         self._grid_to_image = template.grid_image.instantiate_grid_to_image(
             command_queue, grid_shape, lm_scale, lm_bias, fft_plan, allocator)
         # lm_bias = -pixels / 2 * lm_scale above and the taper of grid.ConvolutionKernel is an
-        # even function sampled symmetrically: one quadrant of the factor plane is enough
-        self._grid_to_image.symmetric_factors = pixels % 2 == 0
+        # even function sampled symmetrically, so one quadrant of the factor plane would do
+        # (GridToImage.symmetric_factors: 2 % faster, a quarter of the memory).  Left off: a
+        # mirrored pixel then gets the factor of its partner, whose direction cosine differs in
+        # the last bit, and at w = 2e4 wavelengths that moves single pixels at the image edge
+        # (where the taper division amplifies everything) by 3e-3 of the peak against the host
+        # result instead of 2e-4 (profiles/r02_transform.md).
+        self._grid_to_image.symmetric_factors = False
         self._psf_patch = instantiate(template.psf_patch, image_shape)
         self._noise_est = instantiate(template.noise_est, image_shape,
                                       template.clean_parameters.border)
