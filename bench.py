@@ -710,7 +710,8 @@ def run_gpu(args, ranks):
         gbs = nbytes / (secs / count) / 1e9
         return {'kernel': kernel, 'label': name, 'bound': 'hbm', 'achieved': gbs,
                 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
-                'traffic': traffic.get(traffic_key), 'peak_source': hbm_source,
+                'traffic': traffic.get(traffic_key), 'traffic_note': traffic.get('note'),
+                'peak_source': hbm_source,
                 'bytes_per_launch': nbytes, 'avg_launch_ms': secs / count * 1e3,
                 'launches_per_step': count / args.steps, 'ms_per_step': secs / args.steps * 1e3,
                 'note': note}
