@@ -466,8 +466,10 @@ class Imaging(accel.OperationSequence):
         """Zero `buffer` (whole, or the column groups of `occupancy`) on `queue`; returns what
         :meth:`_clear_covers` compares."""
         with profile_device(queue, 'clear_grid'):
-            if occupancy is None or buffer.dtype != np.complex64:
-                buffer.zero(queue)
+            pitch, plane = buffer.padded_shape[2], buffer.padded_shape[1] * buffer.padded_shape[2]
+            if (occupancy is None or buffer.dtype != np.complex64 or pitch % 2 or plane % 2
+                    or (buffer.ptr.value or 0) % 16):
+                buffer.zero(queue)          # (kib_clear_columns wants 16-byte aligned pairs)
                 return None
             _lib.call('kib_clear_columns', buffer.ptr, buffer.padded_shape[2],
                       buffer.padded_shape[1] * buffer.padded_shape[2], buffer.shape[2],
@@ -532,7 +534,12 @@ class Imaging(accel.OperationSequence):
         of the grid -> image transform are kept across the passes over this channel
         (:attr:`.image.GridToImage.factor_cache_planes`) and dropped here."""
         self._grid_to_image.clear_factor_cache()
-        self._grid_to_image.factor_cache_planes = int(w_slices)
+        dirty = self.buffer('dirty')
+        plane_bytes = (2 * dirty.dtype.itemsize * dirty.shape[1] * dirty.shape[2]
+                       if dirty is not None else 1)
+        # at most 24 GB of tables (fewer planes than W slices would only thrash: none then)
+        fits = int(w_slices) * plane_bytes <= 24 << 30
+        self._grid_to_image.factor_cache_planes = int(w_slices) if fits else 0
         if getattr(self, '_spare_zeroed', None) is not None:
             # the look-ahead clear of the second grid buffer reads an occupancy mask that the
             # new channel may be about to refill in place

@@ -244,3 +244,46 @@ def test_clean_helpers():
     for fn in (clean.metric_to_power, clean.power_to_metric):
         with pytest.raises(ValueError):
             fn(2, 1.0)
+
+
+def test_column_occupancy_fractions_match_brute_force():
+    """bench.column_occupancy_fractions (the byte accounting of the rooflines) against a
+    cell-by-cell count of the footprints."""
+    import bench
+    rs = np.random.RandomState(11)
+    grid_size = 1230
+    K = bench.KERNEL_WIDTH
+    bias = (K - 1) // 2 - grid_size // 2
+    dtype = np.dtype([('uv', np.int16, (2,))])
+    slices = []
+    for n in (0, 1, 40, 3000):
+        s = np.zeros(n, dtype).view(np.recarray)
+        s.uv[:, 0] = rs.randint(-grid_size // 2 - 20, grid_size // 2 + 20, n)
+        slices.append(s)
+    got = bench.column_occupancy_fractions(slices, grid_size)
+    groups = (grid_size + 7) // 8
+    for s, fraction in zip(slices, got):
+        mask = np.zeros(groups, bool)
+        for u in s.uv[:, 0].astype(int):
+            u0 = u - bias
+            if u0 < 0 or u0 + K > grid_size:
+                continue
+            for c in range(u0, u0 + K):
+                mask[c >> 3] = True
+        assert fraction == pytest.approx(mask.sum() / groups)
+
+
+def test_grid_clear_bookkeeping():
+    """Imaging._clear_covers: a clear made for one occupancy mask only serves that very mask
+    (same object, not refilled since); a whole-buffer clear serves everything."""
+    from katsdpimager_b200.imaging import Imaging
+
+    class Mask:
+        generation = 0
+    a, b = Mask(), Mask()
+    assert Imaging._clear_covers(None, None) and Imaging._clear_covers(None, a)
+    assert Imaging._clear_covers((a, 0), a)
+    assert not Imaging._clear_covers((a, 0), b)
+    assert not Imaging._clear_covers((a, 0), None)
+    a.generation = 1                # refilled in place for another channel
+    assert not Imaging._clear_covers((a, 0), a)
