@@ -286,10 +286,16 @@ def make_dirty(imager, vis, field, mid_w, vis_block, degrid, full_cycle=False,
         for w_slice in w_slices:
             masks[w_slice] = vis.occupancy(imager.command_queue, w_slice, imager.kernel_width,
                                            imager.buffer('grid').shape[-1])
+    # the masks are made for the gridder's grid; the degridder's has the same geometry unless
+    # somebody bound another one
+    same_degrid_grid = False
+    if masks and full_cycle and degrid:
+        same_degrid_grid = (imager.buffer('degrid') is not None
+                            and imager.buffer('degrid').shape == imager.buffer('grid').shape)
     for i, w_slice in enumerate(w_slices):
         occupancy = masks.get(w_slice)
         if full_cycle and degrid:
-            if occupancy is not None:
+            if occupancy is not None and same_degrid_grid:
                 # (the model only changes between passes)
                 imager.model_to_grid(mid_w[w_slice], occupancy=occupancy, model_unchanged=i > 0)
             else:

@@ -287,3 +287,89 @@ def test_grid_clear_bookkeeping():
     assert not Imaging._clear_covers((a, 0), None)
     a.generation = 1                # refilled in place for another channel
     assert not Imaging._clear_covers((a, 0), a)
+
+
+def test_make_dirty_call_sequence():
+    """pipeline.make_dirty replays frontend.make_dirty (reference frontend.py:110-149): per
+    non-empty W slice model_to_grid, clear_grid, (feed, predict, grid) per chunk, grid_to_image;
+    with resident records every call carries the slice's occupancy mask, the clear also the
+    next slice's (wrapping to the first: the next pass), and only the first model_to_grid of
+    a pass looks for the model's empty rows."""
+    from katsdpimager_b200 import pipeline
+
+    class Buffer:
+        shape = (4, 64, 64)
+
+    class FakeImager:
+        command_queue = None
+
+        def __init__(self, with_kernel_width=True):
+            self.calls = []
+            if with_kernel_width:
+                self.kernel_width = 7
+
+        def buffer(self, name):
+            return Buffer()
+
+        def __getattr__(self, name):
+            if name.startswith('_') or name == 'kernel_width':
+                raise AttributeError(name)
+
+            def record(*args, **kwargs):
+                self.calls.append((name, args, kwargs))
+            return record
+
+    class FakeVis:
+        counts = [5, 0, 3, 2]
+        num_w_slices = 4
+
+        def len(self, w_slice):
+            return self.counts[w_slice]
+
+        def chunks(self, w_slice, block):
+            n = self.counts[w_slice]
+            return [(s, min(block, n - s)) for s in range(0, n, block)]
+
+        def occupancy(self, queue, w_slice, kernel_width, grid_size):
+            assert (kernel_width, grid_size) == (7, 64)
+            return 'mask%d' % w_slice
+
+        def feed(self, imager, w_slice, start, count, field, with_weights):
+            imager.calls.append(('feed', (w_slice, start, count, field, with_weights), {}))
+
+    mid_w = [0.0, 1.0, 2.0, 3.0]
+    imager = FakeImager()
+    pipeline.make_dirty(imager, FakeVis(), 'vis', mid_w, 4, True, full_cycle=True)
+    names = [c[0] for c in imager.calls]
+    assert names == ['clear_dirty',
+                     'model_to_grid', 'clear_grid', 'feed', 'predict', 'grid', 'feed', 'predict',
+                     'grid', 'grid_to_image',
+                     'model_to_grid', 'clear_grid', 'feed', 'predict', 'grid', 'grid_to_image',
+                     'model_to_grid', 'clear_grid', 'feed', 'predict', 'grid', 'grid_to_image']
+    by_name = {}
+    for name, args, kwargs in imager.calls:
+        by_name.setdefault(name, []).append((args, kwargs))
+    assert [k for _, k in by_name['clear_grid']] == [
+        {'occupancy': 'mask0', 'next_occupancy': 'mask2'},
+        {'occupancy': 'mask2', 'next_occupancy': 'mask3'},
+        {'occupancy': 'mask3', 'next_occupancy': 'mask0'}]
+    assert by_name['model_to_grid'] == [
+        ((0.0,), {'occupancy': 'mask0', 'model_unchanged': False}),
+        ((2.0,), {'occupancy': 'mask2', 'model_unchanged': True}),
+        ((3.0,), {'occupancy': 'mask3', 'model_unchanged': True})]
+    assert by_name['grid_to_image'] == [((0.0,), {'occupancy': 'mask0'}),
+                                        ((2.0,), {'occupancy': 'mask2'}),
+                                        ((3.0,), {'occupancy': 'mask3'})]
+    assert by_name['feed'][0][0] == (0, 0, 4, 'vis', True)
+    assert by_name['feed'][1][0] == (0, 4, 1, 'vis', True)
+    # PSF pass without degridding calls, occupancy switched off: the reference's plain calls
+    imager = FakeImager()
+    pipeline.make_dirty(imager, FakeVis(), 'weights', mid_w, 8, True, use_occupancy=False)
+    assert [c[0] for c in imager.calls] == ['clear_dirty'] + ['clear_grid', 'feed', 'grid',
+                                                              'grid_to_image'] * 3
+    assert all(not kwargs for _, _, kwargs in imager.calls)
+    # an imager without the extensions (the reference's own Imaging): plain calls as well
+    imager = FakeImager(with_kernel_width=False)
+    pipeline.make_dirty(imager, FakeVis(), 'vis', mid_w, 8, True, full_cycle=True)
+    assert all(not kwargs for _, _, kwargs in imager.calls)
+    assert [c[0] for c in imager.calls].count('model_to_grid') == 3
